@@ -1,0 +1,695 @@
+// ef_api.cu -- C ABI (include/ef_b200.h): handle, workspace planner, level geometry, parameter
+// tables, stage sequencing.  Host side of the hot path; mirrors the orchestration of
+// EfficientFeaturesImpl::detectAndComputeAsync (src/cuda_efficient_features.cpp:225-321) without its
+// two host synchronisations per level.
+#include "ef_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "params/ef_bad_tables.inc"
+#include "params/ef_hashsift_w256.inc"
+#include "params/ef_hashsift_w512.inc"
+
+unsigned long long g_ef_launches = 0;
+
+namespace {
+
+struct Geometry {
+    int nlevels = 0;
+    int w[EF_MAX_LEVELS], h[EF_MAX_LEVELS];
+    float scale[EF_MAX_LEVELS];
+    int quota[EF_MAX_LEVELS];
+};
+
+// calcImagePyramid sizes (cuda_efficient_features.cpp:144-155) and calcNumFeaturesPerLevel (:159-174)
+void compute_geometry(int w, int h, float scaleFactor, int nlevels, int nfeatures, Geometry& g)
+{
+    g.nlevels = nlevels;
+    float scale = 1.f;
+    g.w[0] = w; g.h[0] = h; g.scale[0] = scale;
+    for (int s = 1; s < nlevels; s++) {
+        scale *= scaleFactor;
+        const float inv = 1.f / scale;
+        g.h[s] = (int)lrintf(inv * (float)h); // cvRound
+        g.w[s] = (int)lrintf(inv * (float)w);
+        g.scale[s] = scale;
+    }
+    const double factor = (double)(1 / scaleFactor);
+    double nf = nfeatures * (1 - factor) / (1 - std::pow(factor, nlevels));
+    int sum = 0;
+    for (int s = 0; s < nlevels - 1; s++) {
+        g.quota[s] = (int)lrint(nf);
+        sum += g.quota[s];
+        nf *= factor;
+    }
+    g.quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+int desc_bytes_of(int t) { return (t == EF_BAD_256 || t == EF_HASH_SIFT_256) ? 32 : 64; }
+bool is_bad(int t) { return t == EF_BAD_256 || t == EF_BAD_512; }
+
+struct LevelPlan { unsigned long long img_off, blur_off, resp_off, mask_off, rowcnt_off, surv_off, sel_off; int img_pitch, resp_pitch; };
+
+} // namespace
+
+struct ef_handle {
+    ef_params prm;
+    std::string err;
+    int device = 0;
+
+    // workspace plan (for max_width x max_height)
+    Geometry gmax;
+    LevelPlan plan[EF_MAX_LEVELS];
+    unsigned long long rowcnt_bytes = 0; // leading region of every frame slot, zeroed per call
+    unsigned long long slot_bytes = 0;
+    size_t total_bytes = 0;
+
+    uint8_t* d_ws = nullptr;
+    EfLevelCounters* d_counters = nullptr;
+    short2* d_nms_offsets = nullptr;
+    int nms_noffsets = 0, nms_R = 0, nms_r2 = 0, nms_stage_end[4] = { 0, 0, 0, 0 };
+    int nms_radius_built = -1;
+
+    // descriptor tables (per handle, per device)
+    uchar4* d_bad_boxes[2] = { nullptr, nullptr };
+    unsigned char* d_bad_radius[2] = { nullptr, nullptr };
+    float* d_bad_thr[2] = { nullptr, nullptr };
+    float* d_hs_weights_t[2] = { nullptr, nullptr }; // 129 x nbits (transposed)
+    float* d_exp_table = nullptr;
+    float* d_atan2_table = nullptr;
+
+    uint8_t* d_sift128 = nullptr;   // max(max_batch*nfeatures, max_keypoints) x 128
+    float* d_proj = nullptr;        // optional debug: rows x 512
+    bool keep_proj = false;
+    size_t sift_rows = 0;
+
+    // compute-only scratch
+    unsigned* d_integral = nullptr;
+    unsigned* d_segsum = nullptr;
+    float4* d_kpts4 = nullptr;
+
+    // host-API staging
+    uint8_t* d_in = nullptr; size_t in_pitch = 0, in_stride = 0;
+    float* d_out_kpts = nullptr; size_t out_kpts_pitch = 0, out_kpts_stride = 0;
+    uint8_t* d_out_desc = nullptr; size_t out_desc_stride = 0;
+    int* d_out_counts = nullptr;
+    int* h_counts_pinned = nullptr;
+
+    // optional per-stage timing (bench.py): events recorded between the stages
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;      // events consumed since the last ef_stage_times()
+    std::vector<int> ev_stage; // stage id that ENDS at event i (-1 = start marker)
+
+    // last call
+    int last_w = 0, last_h = 0, last_nframes = 0;
+    const uint8_t* last_img0 = nullptr; size_t last_img0_stride = 0; int last_img0_pitch = 0;
+    Geometry glast;
+};
+
+namespace {
+
+int fail(ef_handle* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+
+#define EF_CUDA(h, expr)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return fail(h, EF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+    } while (0)
+
+void free_all(ef_handle* h)
+{
+    cudaFree(h->d_ws); cudaFree(h->d_counters); cudaFree(h->d_nms_offsets);
+    for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); }
+    cudaFree(h->d_exp_table); cudaFree(h->d_atan2_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
+    cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
+    cudaFree(h->d_in); cudaFree(h->d_out_kpts); cudaFree(h->d_out_desc); cudaFree(h->d_out_counts);
+    if (h->h_counts_pinned) cudaFreeHost(h->h_counts_pinned);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    h->ev_pool.clear(); h->ev_stage.clear(); h->ev_used = 0;
+}
+
+int validate(const ef_params& p, std::string& why)
+{
+    if (p.nfeatures < 1) { why = "nfeatures must be >= 1"; return EF_ERR_BAD_ARG; }
+    if (!(p.scale_factor > 1.f)) { why = "scale_factor must be > 1"; return EF_ERR_BAD_ARG; }
+    if (p.nlevels < 1 || p.nlevels > EF_MAX_LEVELS) { why = "nlevels must be in [1,16]"; return EF_ERR_BAD_ARG; }
+    if (p.first_level < 0 || p.first_level >= p.nlevels) { why = "first_level must be in [0,nlevels)"; return EF_ERR_BAD_ARG; }
+    if (p.fast_threshold < 0 || p.fast_threshold > 255) { why = "fast_threshold must be in [0,255]"; return EF_ERR_BAD_ARG; }
+    if (p.nonmax_radius < 0 || p.nonmax_radius > 64) { why = "nonmax_radius must be in [0,64]"; return EF_ERR_BAD_ARG; }
+    if (p.desc_type < EF_BAD_256 || p.desc_type > EF_HASH_SIFT_512) { why = "unknown descriptor type"; return EF_ERR_BAD_ARG; }
+    if (p.max_width < 32 || p.max_height < 32 || p.max_width > 32767 || p.max_height > 32767) { why = "max_width/max_height must be in [32,32767] (short2 locations)"; return EF_ERR_BAD_ARG; }
+    if (p.max_batch < 1) { why = "max_batch must be >= 1"; return EF_ERR_BAD_ARG; }
+    return EF_OK;
+}
+
+// plan the per-frame workspace slot for the largest frame
+void plan_workspace(ef_handle* h)
+{
+    const ef_params& p = h->prm;
+    compute_geometry(p.max_width, p.max_height, p.scale_factor, p.nlevels, p.nfeatures, h->gmax);
+    unsigned long long off = 0;
+    // rowcnt region first (zeroed with one 2-D memset per call)
+    for (int l = 0; l < p.nlevels; l++) { h->plan[l].rowcnt_off = off; off += ef_align_up((unsigned long long)h->gmax.h[l] * 4, 128); }
+    h->rowcnt_bytes = off;
+    for (int l = 0; l < p.nlevels; l++) {
+        LevelPlan& q = h->plan[l];
+        const int w = h->gmax.w[l], hh = h->gmax.h[l];
+        q.img_pitch = (int)ef_align_up(w, 128);
+        q.resp_pitch = (int)ef_align_up(w, 32);
+        const unsigned long long img_bytes = (unsigned long long)q.img_pitch * hh;
+        q.img_off = off; if (l > 0) off += ef_align_up(img_bytes, 256);
+        q.blur_off = off; off += ef_align_up(img_bytes, 256);
+        q.resp_off = off; off += ef_align_up((unsigned long long)q.resp_pitch * hh * 4, 256);
+        const unsigned long long tiles = (unsigned long long)ef_div_up(w, EF_TILE) * ef_div_up(hh, EF_TILE);
+        q.mask_off = off; off += ef_align_up(tiles * EF_TILE * 4, 256);
+        const unsigned long long surv_cap = (unsigned long long)std::max(1l, lrint(0.1 * (double)w * hh));
+        q.surv_off = off; off += ef_align_up(surv_cap * sizeof(EfSurvivor), 256);
+        q.sel_off = off; off += ef_align_up((unsigned long long)p.nfeatures * sizeof(EfSelected), 256);
+    }
+    h->slot_bytes = ef_align_up(off, 4096);
+}
+
+// disc offsets (dx^2+dy^2 < r^2, excluding 0) sorted by Chebyshev ring; radiusSuppression :291-292
+int build_nms_offsets(ef_handle* h)
+{
+    const int radius = h->prm.nonmax_radius;
+    if (h->nms_radius_built == radius) return EF_OK;
+    const float rf = (float)radius;
+    const int r2 = (int)std::ceil(rf * rf);
+    int R = 0;
+    while ((R + 1) * (R + 1) < r2) R++;
+    std::vector<short2> offs;
+    int stage_end[4] = { 0, 0, 0, 0 };
+    const int ring_limit[4] = { 1, 3, 7, 1 << 30 };
+    int prev = 0;
+    for (int st = 0; st < 4; st++) {
+        for (int ring = prev + 1; ring <= std::min(ring_limit[st], R); ring++)
+            for (int dy = -ring; dy <= ring; dy++)
+                for (int dx = -ring; dx <= ring; dx++)
+                    if (std::max(std::abs(dx), std::abs(dy)) == ring && dx * dx + dy * dy < r2) offs.push_back(make_short2((short)dx, (short)dy));
+        stage_end[st] = (int)offs.size();
+        prev = std::min(ring_limit[st], R);
+    }
+    if (!offs.empty())
+        EF_CUDA(h, cudaMemcpy(h->d_nms_offsets, offs.data(), offs.size() * sizeof(short2), cudaMemcpyHostToDevice));
+    h->nms_noffsets = (int)offs.size();
+    h->nms_R = R; h->nms_r2 = r2;
+    std::memcpy(h->nms_stage_end, stage_end, sizeof(stage_end));
+    h->nms_radius_built = radius;
+    return EF_OK;
+}
+
+int upload_tables(ef_handle* h)
+{
+    // BAD tables (bad.p256.h / bad.p512.h via tools/gen_params.py)
+    for (int v = 0; v < 2; v++) {
+        const int nbits = v == 0 ? 256 : 512;
+        const unsigned char(*src)[5] = v == 0 ? ef_bad_boxes_256 : ef_bad_boxes_512;
+        const unsigned int* thr = v == 0 ? ef_bad_thresholds_256_bits : ef_bad_thresholds_512_bits;
+        std::vector<uchar4> boxes(nbits); std::vector<unsigned char> rad(nbits);
+        for (int i = 0; i < nbits; i++) { boxes[i] = make_uchar4(src[i][0], src[i][1], src[i][2], src[i][3]); rad[i] = src[i][4]; }
+        EF_CUDA(h, cudaMalloc(&h->d_bad_boxes[v], nbits * sizeof(uchar4)));
+        EF_CUDA(h, cudaMalloc(&h->d_bad_radius[v], nbits));
+        EF_CUDA(h, cudaMalloc(&h->d_bad_thr[v], nbits * sizeof(float)));
+        EF_CUDA(h, cudaMemcpy(h->d_bad_boxes[v], boxes.data(), nbits * sizeof(uchar4), cudaMemcpyHostToDevice));
+        EF_CUDA(h, cudaMemcpy(h->d_bad_radius[v], rad.data(), nbits, cudaMemcpyHostToDevice));
+        EF_CUDA(h, cudaMemcpy(h->d_bad_thr[v], thr, nbits * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // HashSIFT projection, transposed to 129 x nbits so that one thread per output bit reads coalesced
+    for (int v = 0; v < 2; v++) {
+        const int nbits = v == 0 ? 256 : 512;
+        const unsigned int* wb = v == 0 ? ef_hashsift_w256_bits : ef_hashsift_w512_bits;
+        std::vector<unsigned int> wt((size_t)129 * nbits);
+        for (int j = 0; j < nbits; j++)
+            for (int k = 0; k < 129; k++) wt[(size_t)k * nbits + j] = wb[(size_t)j * 129 + k];
+        EF_CUDA(h, cudaMalloc(&h->d_hs_weights_t[v], wt.size() * sizeof(float)));
+        EF_CUDA(h, cudaMemcpy(h->d_hs_weights_t[v], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // Finite-domain libm tables of the CPU reference (constants, filled once per handle with the host's
+    // libm -- the same libm the reference's CPU build links, which is what "bit-exact vs CPU" means):
+    //   expf(distScale * ((x-15)^2 + (y-15)^2)) for the 30x30 gradient positions (hash_sift.cpp:220-224,247)
+    //   atan2f(dy, dx) for dy, dx in [-255, 255]                                  (hash_sift.cpp:250-254)
+    {
+        std::vector<float> et(900), at((size_t)511 * 511);
+        const float kpScale = 1.f / 6;
+        const float kpRadius = kpScale * 32.f * 0.5f;
+        const float kernelSigma = 0.5f * 4 * 3.f * kpRadius;
+        const float distScale = -1.f / (2 * kernelSigma * kernelSigma);
+        const float cx = 0.5f * 30.f, cy = 0.5f * 30.f;
+        for (int y = 0; y < 30; y++)
+            for (int x = 0; x < 30; x++) {
+                const float fx = (float)x - cx, fy = (float)y - cy;
+                et[y * 30 + x] = expf(distScale * (fx * fx + fy * fy));
+            }
+        for (int dy = -255; dy <= 255; dy++)
+            for (int dx = -255; dx <= 255; dx++) at[(size_t)(dy + 255) * 511 + (dx + 255)] = atan2f((float)dy, (float)dx);
+        EF_CUDA(h, cudaMalloc(&h->d_exp_table, et.size() * sizeof(float)));
+        EF_CUDA(h, cudaMalloc(&h->d_atan2_table, at.size() * sizeof(float)));
+        EF_CUDA(h, cudaMemcpy(h->d_exp_table, et.data(), et.size() * sizeof(float), cudaMemcpyHostToDevice));
+        EF_CUDA(h, cudaMemcpy(h->d_atan2_table, at.data(), at.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return EF_OK;
+}
+
+int allocate(ef_handle* h)
+{
+    const ef_params& p = h->prm;
+    plan_workspace(h);
+    size_t total = 0;
+    auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { total += bytes; return cudaMalloc(ptr, bytes ? bytes : 1); };
+    EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
+    EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
+    EF_CUDA(h, alloc((void**)&h->d_nms_offsets, sizeof(short2) * 129 * 129));
+    h->sift_rows = std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
+    EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
+    EF_CUDA(h, alloc((void**)&h->d_integral, (size_t)(p.max_width + 1) * (p.max_height + 1) * 4));
+    EF_CUDA(h, alloc((void**)&h->d_segsum, (size_t)(p.max_width + 1) * (ef_div_up(p.max_height, 64) + 1) * 4));
+    EF_CUDA(h, alloc((void**)&h->d_kpts4, (size_t)p.max_keypoints * sizeof(float4)));
+    // host-API staging
+    h->in_pitch = ef_align_up(p.max_width, 128);
+    h->in_stride = h->in_pitch * p.max_height;
+    EF_CUDA(h, alloc((void**)&h->d_in, h->in_stride * p.max_batch));
+    h->out_kpts_pitch = ef_align_up((size_t)p.nfeatures * 4, 128);
+    h->out_kpts_stride = h->out_kpts_pitch * EF_ROWS_COUNT;
+    EF_CUDA(h, alloc((void**)&h->d_out_kpts, h->out_kpts_stride * p.max_batch));
+    h->out_desc_stride = (size_t)p.nfeatures * 64;
+    EF_CUDA(h, alloc((void**)&h->d_out_desc, h->out_desc_stride * p.max_batch));
+    EF_CUDA(h, alloc((void**)&h->d_out_counts, sizeof(int) * p.max_batch));
+    EF_CUDA(h, cudaMallocHost((void**)&h->h_counts_pinned, sizeof(int) * (p.max_batch + EF_MAX_LEVELS * 4)));
+    h->total_bytes = total;
+    return EF_OK;
+}
+
+// fill the kernel parameter block for an actual call
+int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
+{
+    const ef_params& p = h->prm;
+    if (w > p.max_width || hh > p.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than max_width x max_height of the handle");
+    if (nframes < 1 || nframes > p.max_batch) return fail(h, EF_ERR_CAPACITY, "nframes exceeds max_batch of the handle");
+    if (w < 32 || hh < 32) return fail(h, EF_ERR_BAD_ARG, "image smaller than 32x32");
+    int rc = build_nms_offsets(h);
+    if (rc != EF_OK) return rc;
+    Geometry& g = h->glast;
+    compute_geometry(w, hh, p.scale_factor, p.nlevels, p.nfeatures, g);
+    std::memset(&P, 0, sizeof(P));
+    P.nlevels = p.nlevels; P.first_level = p.first_level; P.nframes = nframes;
+    P.fast_threshold = p.fast_threshold; P.nms_r2 = h->nms_r2; P.nms_R = h->nms_R; P.nms_noffsets = h->nms_noffsets;
+    std::memcpy(P.nms_stage_end, h->nms_stage_end, sizeof(P.nms_stage_end));
+    P.nfeatures = p.nfeatures;
+    P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
+    P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
+    P.counters = h->d_counters;
+    P.nms_offsets = h->d_nms_offsets;
+    int tiles = 0, btiles = 0, bands = 0, kblocks = 0;
+    for (int l = 0; l < p.nlevels; l++) {
+        EfLevel& L = P.lv[l];
+        const LevelPlan& q = h->plan[l];
+        L.w = g.w[l]; L.h = g.h[l];
+        if (L.w < 1 || L.h < 1) return fail(h, EF_ERR_BAD_ARG, "pyramid level degenerates to zero size; reduce nlevels");
+        L.img_pitch = q.img_pitch; L.blur_pitch = q.img_pitch; L.resp_pitch = q.resp_pitch;
+        L.tiles_x = ef_div_up(L.w, EF_TILE); L.tiles_y = ef_div_up(L.h, EF_TILE);
+        L.blur_tiles_x = ef_div_up(L.w, 64);
+        L.quota = g.quota[l];
+        L.surv_cap = (int)std::max(1l, lrint(0.1 * (double)L.w * L.h)); // CORNER_DENSITY, cuda_efficient_features.cpp:35,252
+        L.scale = g.scale[l];
+        if (l > 0) {
+            L.rx = (float)(1.0 / ((double)L.w / g.w[l - 1]));
+            L.ry = (float)(1.0 / ((double)L.h / g.h[l - 1]));
+        }
+        L.img_off = q.img_off; L.blur_off = q.blur_off; L.resp_off = q.resp_off; L.mask_off = q.mask_off;
+        L.rowcnt_off = q.rowcnt_off; L.surv_off = q.surv_off; L.sel_off = q.sel_off;
+        L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks;
+        if (l >= p.first_level) {
+            tiles += L.tiles_x * L.tiles_y;
+            bands += L.tiles_y;
+            kblocks += ef_div_up(std::min(L.quota, p.nfeatures), 8);
+            btiles += L.blur_tiles_x * ef_div_up(L.h, 32);
+        }
+    }
+    P.total_tiles = tiles; P.total_blur_tiles = btiles; P.total_bands = bands; P.total_kpt_blocks = kblocks;
+    h->last_w = w; h->last_h = hh; h->last_nframes = nframes;
+    return EF_OK;
+}
+
+void mark(ef_handle* h, int stage, cudaStream_t s)
+{
+    if (!h->timing) return;
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->ev_pool.push_back(e);
+        h->ev_stage.push_back(-1);
+    }
+    h->ev_stage[h->ev_used] = stage;
+    cudaEventRecord(h->ev_pool[h->ev_used++], s);
+}
+
+int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
+{
+    EF_CUDA(h, cudaMemset2DAsync(h->d_ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
+    EF_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
+    mark(h, -1, s);
+    ef_launch_pyramid(P, s);      mark(h, EF_STAGE_PYRAMID, s);
+    ef_launch_score(P, s);        mark(h, EF_STAGE_SCORE, s);
+    ef_launch_nms(P, s);          mark(h, EF_STAGE_NMS, s);
+    ef_launch_compact(P, s);      mark(h, EF_STAGE_COMPACT, s);
+    ef_launch_select(P, s);       mark(h, EF_STAGE_SELECT, s);
+    ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);
+    if (want_desc) {
+        ef_launch_blur(P, s);     mark(h, EF_STAGE_BLUR, s);
+        const int v = (P.desc_bytes == 32) ? 0 : 1;
+        if (is_bad(P.desc_type)) {
+            EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
+            ef_launch_bad_pipe(P, t, s);
+            mark(h, EF_STAGE_DESCRIBE, s);
+        } else {
+            EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
+            ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
+            mark(h, EF_STAGE_DESCRIBE, s);
+            ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, h->d_hs_weights_t[v], P.desc_bytes * 8,
+                                             P.desc, (size_t)P.desc_stride, P.desc_pitch, h->keep_proj ? h->d_proj : nullptr, s);
+            mark(h, EF_STAGE_PROJECT, s);
+        }
+    }
+    EF_CUDA(h, cudaGetLastError());
+    return EF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ef_version(void) { return "ef_b200 0.1 (sm_100a)"; }
+
+void ef_default_params(ef_params* p)
+{
+    // defaults of EfficientFeatures::create, include/cuda_efficient_features.h:47-48
+    p->nfeatures = 5000; p->scale_factor = 1.2f; p->nlevels = 8; p->first_level = 0; p->fast_threshold = 20;
+    p->nonmax_radius = 15; p->desc_type = EF_HASH_SIFT_256; p->desc_scale = 1.f;
+    p->max_width = 3840; p->max_height = 2160; p->max_batch = 1; p->max_keypoints = 0; p->device = 0;
+}
+
+int ef_create(const ef_params* params, ef_handle** out)
+{
+    if (!params || !out) return EF_ERR_BAD_ARG;
+    *out = nullptr;
+    ef_handle* h = new (std::nothrow) ef_handle();
+    if (!h) return EF_ERR_CUDA;
+    h->prm = *params;
+    if (h->prm.max_keypoints < h->prm.nfeatures) h->prm.max_keypoints = h->prm.nfeatures;
+    if (!(h->prm.desc_scale > 0.f)) h->prm.desc_scale = 1.f;
+    std::string why;
+    int rc = validate(h->prm, why);
+    if (rc != EF_OK) { std::fprintf(stderr, "ef_create: %s\n", why.c_str()); delete h; return rc; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || params->device >= ndev) {
+        // no CPU fallback: the path only exists as sm_100a kernels
+        std::fprintf(stderr, "ef_create: no usable CUDA device (%s)\n", cudaGetErrorString(cudaGetLastError()));
+        delete h; return EF_ERR_CUDA;
+    }
+    h->device = params->device;
+    if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return EF_ERR_CUDA; }
+    rc = allocate(h);
+    if (rc == EF_OK) rc = upload_tables(h);
+    if (rc == EF_OK) rc = build_nms_offsets(h);
+    if (rc != EF_OK) { std::fprintf(stderr, "ef_create: %s\n", h->err.c_str()); free_all(h); delete h; return rc; }
+    *out = h;
+    return EF_OK;
+}
+
+void ef_destroy(ef_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_all(h);
+    delete h;
+}
+
+int ef_set_param(ef_handle* h, int id, double value)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    ef_params q = h->prm;
+    switch (id) {
+    case EF_PARAM_MAX_FEATURES: q.nfeatures = (int)value; break;
+    case EF_PARAM_SCALE_FACTOR: q.scale_factor = (float)value; break;
+    case EF_PARAM_NLEVELS: q.nlevels = (int)value; break;
+    case EF_PARAM_FIRST_LEVEL: q.first_level = (int)value; break;
+    case EF_PARAM_FAST_THRESHOLD: q.fast_threshold = (int)value; break;
+    case EF_PARAM_NONMAX_RADIUS: q.nonmax_radius = (int)value; break;
+    case EF_PARAM_DESCRIPTOR_TYPE: q.desc_type = (int)value; break;
+    case EF_PARAM_DESC_SCALE: q.desc_scale = (float)value; break;
+    default: return fail(h, EF_ERR_BAD_ARG, "unknown parameter id");
+    }
+    std::string why;
+    int rc = validate(q, why);
+    if (rc != EF_OK) return fail(h, rc, why);
+    const bool replan = q.nfeatures > h->prm.nfeatures || q.nlevels != h->prm.nlevels || q.scale_factor != h->prm.scale_factor;
+    if (q.max_keypoints < q.nfeatures) q.max_keypoints = q.nfeatures;
+    h->prm = q;
+    if (replan) {
+        // capacities changed: re-plan and re-allocate here (setters are not on the hot path)
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        free_all(h);
+        const int dev = h->device; const bool keep = h->keep_proj;
+        *h = ef_handle();
+        h->prm = q; h->device = dev; h->keep_proj = keep;
+        rc = allocate(h);
+        if (rc == EF_OK) rc = upload_tables(h);
+        if (rc == EF_OK && h->keep_proj) rc = ef_debug_keep_projection(h, 1);
+        if (rc != EF_OK) return rc;
+    }
+    return build_nms_offsets(h);
+}
+
+int ef_get_param(const ef_handle* h, int id, double* value)
+{
+    if (!h || !value) return EF_ERR_BAD_ARG;
+    switch (id) {
+    case EF_PARAM_MAX_FEATURES: *value = h->prm.nfeatures; break;
+    case EF_PARAM_SCALE_FACTOR: *value = h->prm.scale_factor; break;
+    case EF_PARAM_NLEVELS: *value = h->prm.nlevels; break;
+    case EF_PARAM_FIRST_LEVEL: *value = h->prm.first_level; break;
+    case EF_PARAM_FAST_THRESHOLD: *value = h->prm.fast_threshold; break;
+    case EF_PARAM_NONMAX_RADIUS: *value = h->prm.nonmax_radius; break;
+    case EF_PARAM_DESCRIPTOR_TYPE: *value = h->prm.desc_type; break;
+    case EF_PARAM_DESC_SCALE: *value = h->prm.desc_scale; break;
+    default: return EF_ERR_BAD_ARG;
+    }
+    return EF_OK;
+}
+
+size_t ef_workspace_bytes(const ef_handle* h) { return h ? h->total_bytes : 0; }
+int ef_descriptor_size(const ef_handle* h) { return h ? desc_bytes_of(h->prm.desc_type) : 0; }
+const char* ef_last_error_string(const ef_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ef_detect_and_compute_batch_async(ef_handle* h, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
+                                      int width, int height, float* d_kpts, size_t kpts_stride, size_t kpts_pitch,
+                                      uint8_t* d_desc, size_t desc_stride, size_t desc_pitch, int* d_counts, void* stream)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (!d_imgs || !d_kpts || !d_counts) return fail(h, EF_ERR_BAD_ARG, "null image / keypoint / count pointer");
+    if (pitch < (size_t)width) return fail(h, EF_ERR_BAD_ARG, "pitch smaller than width");
+    if (kpts_pitch < (size_t)h->prm.nfeatures * 4 || (kpts_pitch & 3)) return fail(h, EF_ERR_BAD_ARG, "kpts_pitch must be >= 4*nfeatures and a multiple of 4");
+    if (d_desc && desc_pitch < (size_t)desc_bytes_of(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EfPipe P;
+    int rc = build_pipe(h, nframes, width, height, P);
+    if (rc != EF_OK) return rc;
+    P.img0 = d_imgs; P.img0_stride = img_stride; P.img0_pitch = (int)pitch;
+    P.kpts = d_kpts; P.kpts_stride = kpts_stride; P.kpts_pitch = (int)kpts_pitch;
+    P.desc = d_desc; P.desc_stride = desc_stride; P.desc_pitch = (int)desc_pitch;
+    P.counts = d_counts;
+    h->last_img0 = d_imgs; h->last_img0_stride = img_stride; h->last_img0_pitch = (int)pitch;
+    return run_pipeline(h, P, d_desc != nullptr, (cudaStream_t)stream);
+}
+
+int ef_detect_and_compute_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                                float* d_kpts, size_t kpts_pitch, uint8_t* d_desc, size_t desc_pitch, int* d_count, void* stream)
+{
+    return ef_detect_and_compute_batch_async(h, 1, d_img, 0, pitch, width, height, d_kpts, 0, kpts_pitch, d_desc, 0, desc_pitch, d_count, stream);
+}
+
+static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height, const float4* d_k4, int n,
+                          uint8_t* d_desc, size_t desc_pitch, cudaStream_t s)
+{
+    const ef_params& p = h->prm;
+    EfDescJob job;
+    job.img = d_img; job.w = width; job.h = height; job.pitch = (int)pitch;
+    job.kpts = d_k4; job.n = n; job.scale = p.desc_scale;
+    job.desc = d_desc; job.desc_pitch = (int)desc_pitch; job.nbits = desc_bytes_of(p.desc_type) * 8;
+    const int v = job.nbits == 256 ? 0 : 1;
+    if (is_bad(p.desc_type)) {
+        ef_launch_integral(d_img, width, height, (int)pitch, h->d_integral, h->d_segsum, s);
+        EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
+        ef_launch_bad_flat(job, h->d_integral, t, s);
+    } else {
+        EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
+        ef_launch_hashsift_features_flat(job, t, h->d_sift128, s);
+        ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, h->d_hs_weights_t[v], job.nbits, d_desc, 0, (int)desc_pitch,
+                                         h->keep_proj ? h->d_proj : nullptr, s);
+    }
+    EF_CUDA(h, cudaGetLastError());
+    return EF_OK;
+}
+
+static int compute_check(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height, const void* kp, int n, uint8_t* d_desc, size_t desc_pitch)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (n == 0) return EF_OK;
+    if (!d_img || !kp || !d_desc || n < 0) return fail(h, EF_ERR_BAD_ARG, "null image / keypoint / descriptor pointer");
+    if (width < 2 || height < 2 || pitch < (size_t)width) return fail(h, EF_ERR_BAD_ARG, "bad image geometry");
+    if (width > h->prm.max_width || height > h->prm.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than the handle was created for");
+    if (n > h->prm.max_keypoints) return fail(h, EF_ERR_CAPACITY, "more keypoints than max_keypoints of the handle");
+    if (desc_pitch < (size_t)desc_bytes_of(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    return -1;
+}
+
+int ef_compute_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                     const float* d_kpts_xysa, int n, uint8_t* d_desc, size_t desc_pitch, void* stream)
+{
+    const int rc = compute_check(h, d_img, pitch, width, height, d_kpts_xysa, n, d_desc, desc_pitch);
+    if (rc != -1) return rc;
+    if (((uintptr_t)d_kpts_xysa & 15) != 0) return fail(h, EF_ERR_BAD_ARG, "keypoint array must be 16-byte aligned");
+    return compute_common(h, d_img, pitch, width, height, reinterpret_cast<const float4*>(d_kpts_xysa), n, d_desc, desc_pitch, (cudaStream_t)stream);
+}
+
+int ef_compute_rows_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                          const float* d_kpts5, size_t kpts_pitch, int n, uint8_t* d_desc, size_t desc_pitch, void* stream)
+{
+    const int rc = compute_check(h, d_img, pitch, width, height, d_kpts5, n, d_desc, desc_pitch);
+    if (rc != -1) return rc;
+    ef_launch_convert_rows(d_kpts5, kpts_pitch, n, h->d_kpts4, (cudaStream_t)stream);
+    return compute_common(h, d_img, pitch, width, height, h->d_kpts4, n, d_desc, desc_pitch, (cudaStream_t)stream);
+}
+
+int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h_imgs, size_t img_stride, size_t pitch,
+                                     int width, int height, float* h_kpts5, uint8_t* h_desc, int* h_counts, void* stream)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (!h_imgs || !h_kpts5 || !h_counts) return fail(h, EF_ERR_BAD_ARG, "null host pointer");
+    if (nframes < 1 || nframes > h->prm.max_batch) return fail(h, EF_ERR_CAPACITY, "nframes exceeds max_batch of the handle");
+    if (width > h->prm.max_width || height > h->prm.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than the handle was created for");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nf = h->prm.nfeatures, db = desc_bytes_of(h->prm.desc_type);
+    // upload (getInputMat, cuda_efficient_features.cpp:71-77)
+    for (int f = 0; f < nframes; f++)
+        EF_CUDA(h, cudaMemcpy2DAsync(h->d_in + f * h->in_stride, h->in_pitch, h_imgs + f * img_stride, pitch, width, height, cudaMemcpyHostToDevice, s));
+    int rc = ef_detect_and_compute_batch_async(h, nframes, h->d_in, h->in_stride, h->in_pitch, width, height,
+                                               h->d_out_kpts, h->out_kpts_stride, h->out_kpts_pitch,
+                                               h_desc ? h->d_out_desc : nullptr, h->out_desc_stride, (size_t)db, h->d_out_counts, s);
+    if (rc != EF_OK) return rc;
+    // the single host synchronisation needed to size the outputs (the reference needs 16 per frame)
+    EF_CUDA(h, cudaMemcpyAsync(h->h_counts_pinned, h->d_out_counts, sizeof(int) * nframes, cudaMemcpyDeviceToHost, s));
+    EF_CUDA(h, cudaStreamSynchronize(s));
+    for (int f = 0; f < nframes; f++) {
+        const int n = h->h_counts_pinned[f];
+        h_counts[f] = n;
+        if (n <= 0) continue;
+        // download (cuda_efficient_features.cpp:316-320); host layout: 5 x nfeatures floats, nfeatures x db bytes per frame
+        EF_CUDA(h, cudaMemcpy2DAsync(h_kpts5 + (size_t)f * EF_ROWS_COUNT * nf, (size_t)nf * 4, (uint8_t*)h->d_out_kpts + f * h->out_kpts_stride,
+                                     h->out_kpts_pitch, (size_t)n * 4, EF_ROWS_COUNT, cudaMemcpyDeviceToHost, s));
+        if (h_desc)
+            EF_CUDA(h, cudaMemcpyAsync(h_desc + (size_t)f * nf * db, h->d_out_desc + f * h->out_desc_stride, (size_t)n * db, cudaMemcpyDeviceToHost, s));
+    }
+    EF_CUDA(h, cudaStreamSynchronize(s));
+    return EF_OK;
+}
+
+int ef_detect_and_compute_host(ef_handle* h, const uint8_t* h_img, size_t pitch, int width, int height,
+                               float* h_kpts5, uint8_t* h_desc, int* h_count, void* stream)
+{
+    return ef_detect_and_compute_host_batch(h, 1, h_img, 0, pitch, width, height, h_kpts5, h_desc, h_count, stream);
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+int ef_debug_level_view(const ef_handle* h, int frame, int level, ef_level_view* out)
+{
+    if (!h || !out || level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->prm.max_batch || h->last_w == 0) return EF_ERR_BAD_ARG;
+    const LevelPlan& q = h->plan[level];
+    const uint8_t* slot = h->d_ws + (size_t)frame * h->slot_bytes;
+    out->width = h->glast.w[level]; out->height = h->glast.h[level];
+    out->scale = h->glast.scale[level]; out->quota = h->glast.quota[level];
+    if (level == 0) { out->d_image = h->last_img0 + (size_t)frame * h->last_img0_stride; out->image_pitch = (size_t)h->last_img0_pitch; }
+    else { out->d_image = slot + q.img_off; out->image_pitch = (size_t)q.img_pitch; }
+    out->d_blurred = slot + q.blur_off; out->blurred_pitch = (size_t)q.img_pitch;
+    out->d_response = reinterpret_cast<const float*>(slot + q.resp_off); out->response_pitch = (size_t)q.resp_pitch;
+    return EF_OK;
+}
+
+int ef_debug_level_counts(ef_handle* h, int frame, int* h_counts3, void* stream)
+{
+    if (!h || !h_counts3 || frame < 0 || frame >= h->prm.max_batch) return EF_ERR_BAD_ARG;
+    EfLevelCounters c[EF_MAX_LEVELS];
+    EF_CUDA(h, cudaMemcpyAsync(c, h->d_counters + (size_t)frame * EF_MAX_LEVELS, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    EF_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    for (int l = 0; l < h->prm.nlevels; l++) { h_counts3[3 * l] = c[l].corners; h_counts3[3 * l + 1] = c[l].survivors; h_counts3[3 * l + 2] = c[l].selected; }
+    return EF_OK;
+}
+
+int ef_debug_keep_projection(ef_handle* h, int keep)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (keep && !h->d_proj) EF_CUDA(h, cudaMalloc((void**)&h->d_proj, h->sift_rows * 512 * sizeof(float)));
+    h->keep_proj = keep != 0;
+    return EF_OK;
+}
+
+int ef_debug_hashsift_views(const ef_handle* h, const uint8_t** d_sift128, const float** d_projection)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (d_sift128) *d_sift128 = h->d_sift128;
+    if (d_projection) *d_projection = h->d_proj;
+    return EF_OK;
+}
+
+int ef_stage_timing_enable(ef_handle* h, int enable)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    h->timing = enable != 0;
+    h->ev_used = 0;
+    return EF_OK;
+}
+
+int ef_stage_times(ef_handle* h, float* ms_sum, int* ncalls)
+{
+    if (!h || !ms_sum) return EF_ERR_BAD_ARG;
+    for (int i = 0; i < EF_NUM_STAGES; i++) ms_sum[i] = 0.f;
+    int calls = 0;
+    if (h->ev_used) EF_CUDA(h, cudaEventSynchronize(h->ev_pool[h->ev_used - 1]));
+    for (size_t i = 0; i < h->ev_used; i++) {
+        if (h->ev_stage[i] < 0) { calls++; continue; }
+        float ms = 0.f;
+        EF_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[i - 1], h->ev_pool[i]));
+        ms_sum[h->ev_stage[i]] += ms;
+    }
+    if (ncalls) *ncalls = calls;
+    h->ev_used = 0;
+    return EF_OK;
+}
+
+unsigned long long ef_kernel_launch_count(void) { return g_ef_launches; }
+
+int ef_debug_copy_to_host(ef_handle* h, void* dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes, size_t rows)
+{
+    if (!h || !dst || !d_src) return EF_ERR_BAD_ARG;
+    EF_CUDA(h, cudaDeviceSynchronize());
+    EF_CUDA(h, cudaMemcpy2D(dst, dst_pitch, d_src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+} // extern "C"

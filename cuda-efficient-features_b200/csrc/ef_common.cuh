@@ -1,0 +1,138 @@
+// ef_common.cuh -- shared device/host definitions of the B200 detectAndCompute pipeline.
+//
+// Everything in csrc/ is compiled with -fmad=false: no implicit contraction anywhere.  Where the
+// canonical arithmetic has a fused multiply-add (the pattern nvcc emits for the reference's CUDA
+// detector) it is written as an explicit fmaf(); where the canonical
+// arithmetic is the reference's CPU build (generic x86-64, no FMA: BAD and HashSIFT) plain
+// operators are used and stay unfused.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/ef_b200.h"
+
+#define EF_HALF_PATCH 15          // HALF_PATCH_SIZE, cuda_efficient_features.cpp:34 (border mask, IC radius)
+#define EF_PATCH_SIZE 31.f        // PATCH_SIZE, cuda_efficient_features.cu:36
+#define EF_TILE 32                // square pixel tile of the score / NMS kernels
+#define EF_NEG_INF (__int_as_float(0xff800000))
+
+struct __align__(8) EfSurvivor { short x, y; float resp; };                 // compacted NMS survivor
+struct __align__(16) EfSelected { short x, y; float resp; float angle; int pad; }; // per-level selected keypoint (level coords)
+
+// per-frame, per-level counters (zeroed at the start of every call)
+struct EfLevelCounters { int corners; int survivors; int selected; int overflow; };
+
+struct EfLevel {
+    int w, h;
+    int img_pitch;      // bytes, internal pyramid level (level 0: caller's pitch)
+    int blur_pitch;     // bytes
+    int resp_pitch;     // floats
+    int tiles_x, tiles_y;
+    int tile_start;     // first tile index of this level in the all-level tile table
+    int blur_tile_start, blur_tiles_x; // 64x32 blur tiles
+    int band_start;     // first 32-row band index of this level
+    int quota;          // nfeaturesPerLevel_[s]
+    int surv_cap;       // capacity of the survivor list
+    int kpt_block_start;// first descriptor-CTA index of this level (quota / kpts-per-CTA, rounded up)
+    float scale;        // scales_[s]
+    float rx, ry;       // resize ratios src/dst for producing THIS level from the previous one
+    // byte offsets inside one frame slot of the workspace
+    unsigned long long img_off, blur_off, resp_off, mask_off, rowcnt_off, surv_off, sel_off;
+};
+
+struct EfPipe {
+    int nlevels, first_level, nframes;
+    int fast_threshold, nms_r2, nms_R, nms_noffsets;
+    int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks;
+    int nfeatures;              // output capacity (columns)
+    int desc_type, desc_bytes;
+    // caller buffers (frame f at base + f*stride)
+    const uint8_t* img0; unsigned long long img0_stride; int img0_pitch;
+    float* kpts; unsigned long long kpts_stride; int kpts_pitch;      // bytes
+    uint8_t* desc; unsigned long long desc_stride; int desc_pitch;    // bytes
+    int* counts;
+    // workspace
+    uint8_t* ws; unsigned long long ws_stride;           // per-frame slot
+    EfLevelCounters* counters; /* [frame][EF_MAX_LEVELS] */
+    const short2* nms_offsets;                            // disc offsets sorted by Chebyshev ring
+    int nms_stage_end[4];                                 // offsets [0,e0) ring<=1, [e0,e1) ring<=3, [e1,e2) ring<=7, rest
+    EfLevel lv[EF_MAX_LEVELS];
+};
+
+__host__ __device__ inline int ef_div_up(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline unsigned long long ef_align_up(unsigned long long v, unsigned long long a) { return (v + a - 1) / a * a; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ const uint8_t* ef_level_image(const EfPipe& p, int frame, int level, int& pitch)
+{
+    if (level == 0) { pitch = p.img0_pitch; return p.img0 + (unsigned long long)frame * p.img0_stride; }
+    pitch = p.lv[level].img_pitch;
+    return p.ws + (unsigned long long)frame * p.ws_stride + p.lv[level].img_off;
+}
+__device__ __forceinline__ uint8_t* ef_ws(const EfPipe& p, int frame, unsigned long long off)
+{
+    return p.ws + (unsigned long long)frame * p.ws_stride + off;
+}
+// saturate_cast<uchar>(float) of OpenCV CUDA: cvt.rni.sat.u8.f32
+__device__ __forceinline__ unsigned ef_sat_u8_rne(float v)
+{
+    unsigned r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ int ef_reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+// order-preserving map float -> uint32 (larger float <=> larger key)
+__device__ __forceinline__ unsigned ef_float_key(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+#endif
+
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+extern unsigned long long g_ef_launches;
+#define EF_COUNT_LAUNCH(n) (g_ef_launches += (unsigned long long)(n))
+
+// ---- launchers (host) ----------------------------------------------------------------------------
+void ef_launch_pyramid(const EfPipe& p, cudaStream_t s);
+void ef_launch_score(const EfPipe& p, cudaStream_t s);
+void ef_launch_nms(const EfPipe& p, cudaStream_t s);
+void ef_launch_compact(const EfPipe& p, cudaStream_t s);
+void ef_launch_select(const EfPipe& p, cudaStream_t s);
+void ef_launch_angle_pack(const EfPipe& p, cudaStream_t s);
+void ef_launch_blur(const EfPipe& p, cudaStream_t s);
+
+// descriptor stage: keypoints either from the per-level selected lists (detectAndCompute) or from a
+// flat caller array (compute-only API)
+struct EfDescJob {
+    // image
+    const uint8_t* img; int w, h, pitch;
+    // keypoints: n x float4 (x, y, size, angle)
+    const float4* kpts; int n;
+    float scale;             // BAD scaleFactor / HashSIFT croppingScale
+    uint8_t* desc; int desc_pitch;
+    int nbits;
+};
+struct EfBadTables { const uchar4* boxes_xyxy; const unsigned char* radius; const float* thresholds; };
+
+void ef_launch_integral(const uint8_t* img, int w, int h, int pitch, unsigned* integral, unsigned* segsum, cudaStream_t s);
+void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const EfBadTables& t, cudaStream_t s);
+void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s);
+
+struct EfHashSiftTables { const float* exp_table; /*30x30*/ const float* atan2_table; /*511x511*/ const float* weights; /*nbits x 129*/ };
+void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
+void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
+// projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8); row_map == nullptr: desc row i = i.
+void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const float* weights, int nbits,
+                                uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s);
+void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
+                                      uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s);
+// 5xN keypoint rows -> n x float4 (x, y, 31, angle): convertKeypointsKernel, cuda_efficient_features.cu:250-263
+void ef_launch_convert_rows(const float* kpts5, size_t kpts_pitch, int n, float4* out, cudaStream_t s);

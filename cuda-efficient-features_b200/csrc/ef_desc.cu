@@ -1,0 +1,612 @@
+// ef_desc.cu -- BAD and HashSIFT descriptor kernels (sm_100a), bit-exact restatement targets:
+//   BAD      modules/efficient_features/src/bad.cpp:86-157,166-251,320-405   (CPU ground truth)
+//   HashSIFT modules/efficient_features/src/hash_sift.cpp:68-138,150-198,200-331,353-378
+// They replace the reference's GPU kernels src/cuda_bad.cu:246-316 (+ cudev integral :350-363) and
+// src/cuda_hash_sift.cu:380-435 (+ cublasSgemm, cuda_hash_sift.cpp:44-60), which are NOT bit-exact
+// against the CPU code (float trig, smem float atomics, fp32 SGEMM).
+//
+// Compiled with -fmad=false: the CPU reference is a generic x86-64 build without FMA, so every
+// a*b+c below must stay two roundings.
+#include "ef_common.cuh"
+
+#include <cfloat>
+
+#define EF_DESC_WARPS 8
+
+// =================================================================================================
+// integral image (generic compute-only path; cv::integral / cudev integral, wrapping uint32)
+//   I is (h+1) x (w+1), dense pitch iw = w+1.
+// =================================================================================================
+#define EF_INT_SEG 64
+
+__global__ void __launch_bounds__(256) ef_integral_rows_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch,
+                                                               unsigned* __restrict__ I)
+{
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_carry;
+    const int y = blockIdx.x; // 0..h  (row h of the grid zeroes I row 0)
+    const int iw = w + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (y == h) {
+        for (int x = tid; x < iw; x += 256) I[x] = 0;
+        return;
+    }
+    unsigned* out = I + (size_t)(y + 1) * iw;
+    const uint8_t* row = img + (size_t)y * pitch;
+    if (tid == 0) { s_carry = 0; out[0] = 0; }
+    __syncthreads();
+    for (int x0 = 0; x0 < w; x0 += 1024) {
+        const int x = x0 + tid * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (x + j < w) ? row[x + j] : 0u;
+        v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+        unsigned inc = v[3];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int k = 0; k < warp; k++) woff += s_warp[k];
+        const unsigned base = s_carry + woff + inc - v[3];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (x + j < w) out[x + j + 1] = base + v[j];
+        __syncthreads();
+        if (tid == 255) s_carry = base + v[3];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) ef_integral_segsum_kernel(const unsigned* __restrict__ I, int w, int h, unsigned* __restrict__ segsum)
+{
+    const int iw = w + 1;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int seg = blockIdx.y;
+    if (x >= iw) return;
+    const int ya = 1 + seg * EF_INT_SEG, yb = min(ya + EF_INT_SEG, h + 1);
+    unsigned s = 0;
+    for (int y = ya; y < yb; y++) s += I[(size_t)y * iw + x];
+    segsum[(size_t)seg * iw + x] = s;
+}
+
+__global__ void __launch_bounds__(128) ef_integral_segscan_kernel(int w, int nseg, unsigned* __restrict__ segsum)
+{
+    const int iw = w + 1;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= iw) return;
+    unsigned run = 0;
+    for (int s = 0; s < nseg; s++) {
+        const unsigned v = segsum[(size_t)s * iw + x];
+        segsum[(size_t)s * iw + x] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(128) ef_integral_cols_kernel(unsigned* __restrict__ I, int w, int h, const unsigned* __restrict__ segoff)
+{
+    const int iw = w + 1;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int seg = blockIdx.y;
+    if (x >= iw) return;
+    const int ya = 1 + seg * EF_INT_SEG, yb = min(ya + EF_INT_SEG, h + 1);
+    unsigned run = segoff[(size_t)seg * iw + x];
+    for (int y = ya; y < yb; y++) {
+        run += I[(size_t)y * iw + x];
+        I[(size_t)y * iw + x] = run;
+    }
+}
+
+void ef_launch_integral(const uint8_t* img, int w, int h, int pitch, unsigned* integral, unsigned* segsum, cudaStream_t s)
+{
+    const int iw = w + 1;
+    const int nseg = ef_div_up(h, EF_INT_SEG);
+    ef_integral_rows_kernel<<<h + 1, 256, 0, s>>>(img, w, h, pitch, integral);
+    EF_COUNT_LAUNCH(1);
+    ef_integral_segsum_kernel<<<dim3(ef_div_up(iw, 128), nseg), 128, 0, s>>>(integral, w, h, segsum);
+    EF_COUNT_LAUNCH(1);
+    ef_integral_segscan_kernel<<<ef_div_up(iw, 128), 128, 0, s>>>(w, nseg, segsum);
+    EF_COUNT_LAUNCH(1);
+    ef_integral_cols_kernel<<<dim3(ef_div_up(iw, 128), nseg), 128, 0, s>>>(integral, w, h, segsum);
+    EF_COUNT_LAUNCH(1);
+}
+
+// =================================================================================================
+// BAD
+// =================================================================================================
+struct EfBadAffine { float m00, m01, m02, m10, m11, m12, s; bool border; };
+
+// rectifyBoxes (bad.cpp:121-147) + isKeypointInTheBorder (bad.cpp:92-102)
+__device__ __forceinline__ EfBadAffine ef_bad_affine(float kx, float ky, float size, float angle, float scaleFactor, int w, int h)
+{
+    EfBadAffine a;
+    const float s = scaleFactor * size / (0.5f * (float)(32 + 32));
+    if (angle == -1) {
+        a.m00 = s; a.m01 = 0.0f; a.m02 = -0.5f * s * 32.f + kx;
+        a.m10 = 0.0f; a.m11 = s; a.m12 = -s * 0.5f * 32.f + ky;
+    } else {
+        // double cos/sin exactly like the CPU code (bad.cpp:29,138-139)
+        const float cosine = (angle >= 0) ? (float)cos((double)angle * 0.017453292519943295) : 1.f;
+        const float sine = (angle >= 0) ? (float)sin((double)angle * 0.017453292519943295) : 0.f;
+        a.m00 = s * cosine; a.m01 = -s * sine;
+        a.m02 = (-s * cosine + s * sine) * 32.f * 0.5f + kx;
+        a.m10 = s * sine; a.m11 = s * cosine;
+        a.m12 = (-s * sine - s * cosine) * 32.f * 0.5f + ky;
+    }
+    a.s = s;
+    const float sb = scaleFactor * size / (float)(32 + 32);
+    const float bw = 32.f * sb * 1.75f, bh = 32.f * sb * 1.75f;
+    bool border = false;
+    if (kx < bw || kx + bw >= (float)w) border = true;
+    if (ky < bh || ky + bh >= (float)h) border = true;
+    a.border = border;
+    return a;
+}
+
+// integral accessors: I(y, x) with x in [0,w], y in [0,h]
+struct EfGlobalIntegral {
+    const unsigned* I; int iw;
+    __device__ __forceinline__ unsigned at(int y, int x) const { return __ldg(I + (size_t)y * iw + x); }
+};
+struct EfWindowIntegral { // local integral of the (2*HALF) x (2*HALF) pixel window around an integer keypoint
+    const unsigned* W; int wx0, wy0, pitch;
+    __device__ __forceinline__ unsigned at(int y, int x) const { return W[(y - wy0) * pitch + (x - wx0)]; }
+};
+
+template <class Integral>
+__device__ __forceinline__ bool ef_bad_bit(const Integral& I, const EfBadAffine& a, uchar4 b, int r0, float thr, int w, int h)
+{
+    // bad.cpp:151-155 (CV_ROUNDNUM truncates)
+    const float bx1 = (float)b.x, by1 = (float)b.y, bx2 = (float)b.z, by2 = (float)b.w;
+    const int x1 = __float2int_rz(a.m00 * bx1 + a.m01 * by1 + a.m02 + 0.5f);
+    const int y1 = __float2int_rz(a.m10 * bx1 + a.m11 * by1 + a.m12 + 0.5f);
+    const int x2 = __float2int_rz(a.m00 * bx2 + a.m01 * by2 + a.m02 + 0.5f);
+    const int y2 = __float2int_rz(a.m10 * bx2 + a.m11 * by2 + a.m12 + 0.5f);
+    const int r = __float2int_rz(a.s * (float)r0 + 0.5f);
+    if (!a.border) {
+        // bad.cpp:371-393: integer box sums, threshold scaled by the box area
+        const int side = 1 + (r << 1);
+        const unsigned acc = I.at(y1 - r, x1 - r) + I.at(y1 + r + 1, x1 + r + 1) - I.at(y1 - r, x1 + r + 1) - I.at(y1 + r + 1, x1 - r)
+                           - I.at(y2 - r, x2 - r) - I.at(y2 + r + 1, x2 + r + 1) + I.at(y2 - r, x2 + r + 1) + I.at(y2 + r + 1, x2 - r);
+        return (float)(int)acc <= (thr * (float)(side * side));
+    }
+    // bad.cpp:166-251: clamped boxes, float means.  frameWidth/Height = integral dims (w+1, h+1)
+    const int fw = w + 1, fh = h + 1;
+    int ax1 = x1 - r; if (ax1 < 0) ax1 = 0; else if (ax1 >= fw - 1) ax1 = fw - 2;
+    int ay1 = y1 - r; if (ay1 < 0) ay1 = 0; else if (ay1 >= fh - 1) ay1 = fh - 2;
+    int ax2 = x1 + r + 1; if (ax2 <= 0) ax2 = 1; else if (ax2 >= fw) ax2 = fw - 1;
+    int ay2 = y1 + r + 1; if (ay2 <= 0) ay2 = 1; else if (ay2 >= fh) ay2 = fh - 1;
+    int bx1i = x2 - r; if (bx1i < 0) bx1i = 0; else if (bx1i >= fw - 1) bx1i = fw - 2;
+    int by1i = y2 - r; if (by1i < 0) by1i = 0; else if (by1i >= fh - 1) by1i = fh - 2;
+    int bx2i = x2 + r + 1; if (bx2i <= 0) bx2i = 1; else if (bx2i >= fw) bx2i = fw - 1;
+    int by2i = y2 + r + 1; if (by2i <= 0) by2i = 1; else if (by2i >= fh) by2i = fh - 1;
+    const float sum1 = (float)(int)(I.at(ay1, ax1) + I.at(ay2, ax2) - I.at(ay1, ax2) - I.at(ay2, ax1));
+    const float avg1 = sum1 / (float)((ay2 - ay1) * (ax2 - ax1));
+    const float sum2 = (float)(int)(I.at(by1i, bx1i) + I.at(by2i, bx2i) - I.at(by1i, bx2i) - I.at(by2i, bx1i));
+    const float avg2 = sum2 / (float)((by2i - by1i) * (bx2i - bx1i));
+    return (avg1 - avg2) <= thr;
+}
+
+// one warp = one keypoint; lane l evaluates pairs l, l+32, ...; 32 bits -> 4 bytes, MSB first (bad.cpp:349,368)
+template <class Integral>
+__device__ __forceinline__ void ef_bad_describe(const Integral& I, const EfBadAffine& a, const EfBadTables& t, int nbits,
+                                                int w, int h, uint8_t* out, int lane)
+{
+    for (int g = 0; g < nbits; g += 32) {
+        const int i = g + lane;
+        const bool bit = ef_bad_bit(I, a, t.boxes_xyxy[i], (int)t.radius[i], t.thresholds[i], w, h);
+        const unsigned bal = __brev(__ballot_sync(0xffffffffu, bit)); // pair g+0 -> bit 31
+        if (lane < 4) out[(g >> 3) + lane] = (uint8_t)(bal >> (24 - 8 * lane));
+    }
+}
+
+// ---- generic path: flat keypoint array, global integral image ----------------------------------
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_flat_kernel(const EfDescJob job, const unsigned* __restrict__ integral, const EfBadTables t)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * EF_DESC_WARPS + warp;
+    if (i >= job.n) return;
+    const float4 k = job.kpts[i];
+    const EfBadAffine a = ef_bad_affine(k.x, k.y, k.z, k.w, job.scale, job.w, job.h);
+    EfGlobalIntegral I; I.I = integral; I.iw = job.w + 1;
+    ef_bad_describe(I, a, t, job.nbits, job.w, job.h, job.desc + (size_t)i * job.desc_pitch, lane);
+}
+
+void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const EfBadTables& t, cudaStream_t s)
+{
+    if (job.n <= 0) return;
+    ef_bad_flat_kernel<<<ef_div_up(job.n, EF_DESC_WARPS), EF_DESC_WARPS * 32, 0, s>>>(job, integral, t);
+    EF_COUNT_LAUNCH(1);
+}
+
+// ---- detectAndCompute path: keypoints from the per-level selected lists on the blurred level,
+//      size 31, scale 1 (cuda_efficient_features.cpp:48-69,306).  Every box corner then lies in
+//      [k-22, k+23] (exhaustive over both tables and all angles), so a 48x48-pixel window and its
+//      49x49 local integral in shared memory replace the reference's full-frame integral image.
+#define EF_BW_HALF 24
+#define EF_BW_PIX (2 * EF_BW_HALF)      // 48 pixels
+#define EF_BW_INT (EF_BW_PIX + 1)       // 49 integral entries per side (odd pitch: conflict-free columns)
+
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const __grid_constant__ EfPipe p, const EfBadTables t)
+{
+    extern __shared__ unsigned s_win_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.y;
+    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    int level = p.first_level;
+    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].kpt_block_start) level++;
+    const EfLevel& L = p.lv[level];
+    const int i = (blockIdx.x - L.kpt_block_start) * EF_DESC_WARPS + warp;
+    if (i >= ctr[level].selected) return;
+    int offset = 0;
+    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
+    const int row = offset + i;
+    if (row >= p.nfeatures) return;
+
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
+    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
+    const int pitch = L.blur_pitch;
+    unsigned* W = s_win_all + warp * (EF_BW_INT * EF_BW_INT);
+    const int wx0 = k.x - EF_BW_HALF, wy0 = k.y - EF_BW_HALF;
+
+    // pixels (zero outside the image) into W[j+1][i+1]; first row / column of the integral are zero
+    for (int j = lane; j < EF_BW_INT; j += 32) { W[j] = 0; W[j * EF_BW_INT] = 0; }
+    for (int j = 0; j < EF_BW_PIX; j++) {
+        const int gy = wy0 + j;
+        const bool rowin = gy >= 0 && gy < L.h;
+        for (int c = lane; c < EF_BW_PIX; c += 32) {
+            const int gx = wx0 + c;
+            unsigned v = 0;
+            if (rowin && gx >= 0 && gx < L.w) v = img[(size_t)gy * pitch + gx];
+            W[(j + 1) * EF_BW_INT + c + 1] = v;
+        }
+    }
+    __syncwarp();
+    // column prefix (lane <-> column), then row prefix (lane <-> row)
+    for (int c = lane; c < EF_BW_PIX; c += 32) {
+        unsigned run = 0;
+        for (int j = 1; j <= EF_BW_PIX; j++) { run += W[j * EF_BW_INT + c + 1]; W[j * EF_BW_INT + c + 1] = run; }
+    }
+    __syncwarp();
+    for (int j = 1 + lane; j <= EF_BW_PIX; j += 32) {
+        unsigned run = 0;
+        for (int c = 1; c <= EF_BW_PIX; c++) { run += W[j * EF_BW_INT + c]; W[j * EF_BW_INT + c] = run; }
+    }
+    __syncwarp();
+
+    const EfBadAffine a = ef_bad_affine((float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, L.w, L.h);
+    EfWindowIntegral I; I.W = W; I.wx0 = wx0; I.wy0 = wy0; I.pitch = EF_BW_INT;
+    uint8_t* out = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch;
+    ef_bad_describe(I, a, t, p.desc_bytes * 8, L.w, L.h, out, lane);
+}
+
+void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
+{
+    if (p.total_kpt_blocks <= 0) return;
+    const size_t smem = (size_t)EF_DESC_WARPS * EF_BW_INT * EF_BW_INT * sizeof(unsigned);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ef_bad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    ef_bad_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t);
+    EF_COUNT_LAUNCH(1);
+}
+
+// =================================================================================================
+// HashSIFT features: rectified 32x32 patch -> deterministic 4x4x8 gradient histogram -> 128 u8
+// =================================================================================================
+struct EfSiftSmem {
+    float bf[32];      // fractional row/col bin of patch row r = y+1 (index y), hash_sift.cpp:179-191
+    int bi[32];        // integer bin
+    float mag[900];
+    float of[900];
+    float desc[128];
+    uint8_t patch[32 * 32];
+    uint8_t oi[904];
+};
+
+// hist row/col bin of patch row r = y+1 (hash_sift.cpp:179-180,186-191): scale * (r - 16) + 1.5, scale = 1/8
+__device__ __forceinline__ void ef_sift_bin(int r, int& bi, float& bf)
+{
+    const float kpScale = 1.f / 6;
+    const float cell = 3.f * (kpScale * 32.f * 0.5f);
+    const float scale = 1.f / cell;
+    const float b = scale * ((float)r - 16.f) + 1.5f;
+    bi = (int)floorf(b);
+    bf = b - (float)bi;
+}
+
+// normalize(), hash_sift.cpp:150-160: sequential sum, every lane computes it redundantly
+__device__ __forceinline__ void ef_sift_normalize(float* d, int lane)
+{
+    float sum = 0.f;
+    for (int i = 0; i < 128; i++) { const float v = d[i]; sum += v * v; }
+    const float nrm = fmaxf(sqrtf(sum), FLT_EPSILON);
+    const float scale = 1.f / nrm;
+    __syncwarp();
+    for (int i = lane; i < 128; i += 32) d[i] *= scale;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
+                                                float kx, float ky, float size, float angle, float croppingScale,
+                                                const EfHashSiftTables& t, EfSiftSmem& sm, uint8_t* out128, int lane)
+{
+    if (lane < 30) { int bi; float bf; ef_sift_bin(lane + 1, bi, bf); sm.bi[lane] = bi; sm.bf[lane] = bf; }
+    // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
+    {
+        const float PI_1_0F = 3.14159274f;
+        const float s = croppingScale * size / (0.5f * (float)(32 + 32));
+        const float theta = PI_1_0F * angle / 180;
+        // cosf/sinf: evaluated in double and rounded once (DESIGN.md "transcendentals")
+        const float cost = s * (angle >= 0 ? (float)cos((double)theta) : 1.f);
+        const float sint = s * (angle >= 0 ? (float)sin((double)theta) : 0.f);
+        const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
+        const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
+        const int x = lane;
+        for (int y = 0; y < 32; y++) {
+            const float u = M00 * (float)x + M01 * (float)y + M02;
+            const float v = M10 * (float)x + M11 * (float)y + M12;
+            uint8_t dstVal = 0;
+            const int ui = (int)floorf(u);
+            const int vi = (int)floorf(v);
+            if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
+                const uint8_t* q = img + (size_t)vi * pitch + ui;
+                const float du = u - (float)ui;
+                const float dv = v - (float)vi;
+                const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
+                const float tmp1 = (1 - du) * (float)q[pitch] + du * (float)q[pitch + 1];
+                const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
+                dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
+            }
+            sm.patch[y * 32 + x] = dstVal;
+        }
+    }
+    __syncwarp();
+    // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260). expf over the 30x30 positions and
+    //      atan2f over dy,dx in [-255,255] are finite-domain tables (see ef_api.cu)
+    {
+        const float PI_2_0F = 6.28318548f;
+        const float scaleO = 8 / PI_2_0F;
+        for (int i = lane; i < 900; i += 32) {
+            const int y = i / 30, x = i - y * 30;
+            const int dxi = (int)sm.patch[(y + 1) * 32 + x + 2] - (int)sm.patch[(y + 1) * 32 + x];
+            const int dyi = (int)sm.patch[y * 32 + x + 1] - (int)sm.patch[(y + 2) * 32 + x + 1];
+            const float dx = (float)dxi, dy = (float)dyi;
+            const float mag = t.exp_table[i] * sqrtf(dx * dx + dy * dy);
+            const float ori = t.atan2_table[(dyi + 255) * 511 + (dxi + 255)];
+            const float ob = scaleO * ori;
+            int oi = (int)floorf(ob);
+            const float of = ob - (float)oi;
+            if (oi < 0) oi += 8;
+            if (oi >= 8) oi -= 8;
+            sm.mag[i] = mag;
+            sm.of[i] = of;
+            sm.oi[i] = (uint8_t)oi;
+        }
+    }
+    __syncwarp();
+    // ---- trilinear histogram (hash_sift.cpp:233-290).  lane = (cell, half): cell = hist (rb, cb) in 1..4,
+    //      half 0 owns orientation bins 0..4, half 1 bins 5..8.  Each accumulator receives its
+    //      contributions in raster order of the pixels, exactly like the scalar CPU loop.
+    {
+        const int cell = lane >> 1, half = lane & 1;
+        const int rb = (cell >> 2) + 1, cb = (cell & 3) + 1;
+        const int b0 = half ? 5 : 0;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+        // rows r = y+1 in 1..30 whose bin pair (ri+1, ri+2) contains rb:  ri in {rb-2, rb-1}
+        // scale is exactly 1/8, so bin(r) = (r-16)/8 + 1.5 and the rows feeding hist row rb are
+        // r in [8rb-12, 8rb+3] (clipped to 1..30); the table lookups keep the float expression authoritative.
+        const int ylo = max(8 * rb - 12, 1) - 1, yhi = min(8 * rb + 3, 30) - 1;
+        const int xlo = max(8 * cb - 12, 1) - 1, xhi = min(8 * cb + 3, 30) - 1;
+        for (int y = ylo; y <= yhi; y++) {
+            const int ri = sm.bi[y]; const float rf = sm.bf[y];
+            if (ri + 1 != rb && ri + 2 != rb) continue;
+            const bool r_hi = (ri + 2 == rb);
+            for (int x = xlo; x <= xhi; x++) {
+                const int ci = sm.bi[x]; const float cf = sm.bf[x];
+                if (ci + 1 != cb && ci + 2 != cb) continue;
+                const bool c_hi = (ci + 2 == cb);
+                const int i = y * 30 + x;
+                const float mag = sm.mag[i];
+                const float of = sm.of[i];
+                const int oi = sm.oi[i];
+                // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
+                const float v1 = rf * mag, v0 = mag - v1;
+                const float vr = r_hi ? v1 : v0;
+                const float vc1 = cf * vr, vc0 = vr - vc1;
+                const float vc = c_hi ? vc1 : vc0;
+                const float vo1 = of * vc, vo0 = vc - vo1;
+                const int k = oi - b0; // bin oi gets vo0, bin oi+1 gets vo1
+                acc0 += (k == 0) ? vo0 : ((k == -1) ? vo1 : 0.f);
+                acc1 += (k == 1) ? vo0 : ((k == 0) ? vo1 : 0.f);
+                acc2 += (k == 2) ? vo0 : ((k == 1) ? vo1 : 0.f);
+                acc3 += (k == 3) ? vo0 : ((k == 2) ? vo1 : 0.f);
+                acc4 += (k == 4) ? vo0 : ((k == 3) ? vo1 : 0.f);
+            }
+        }
+        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: oi <= 7)
+        const float bin8 = __shfl_sync(0xffffffffu, acc3, lane | 1); // half 1: acc3 = bin 8
+        const int e = ((rb - 1) * 4 + (cb - 1)) * 8;
+        if (half == 0) {
+            sm.desc[e + 0] = acc0 + bin8;
+            sm.desc[e + 1] = acc1;
+            sm.desc[e + 2] = acc2;
+            sm.desc[e + 3] = acc3;
+            sm.desc[e + 4] = acc4;
+        } else {
+            sm.desc[e + 5] = acc0;
+            sm.desc[e + 6] = acc1;
+            sm.desc[e + 7] = acc2;
+        }
+    }
+    __syncwarp();
+    // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
+    ef_sift_normalize(sm.desc, lane);
+    for (int i = lane; i < 128; i += 32) sm.desc[i] = fminf(sm.desc[i], 0.2f);
+    __syncwarp();
+    ef_sift_normalize(sm.desc, lane);
+    {
+        unsigned packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = __float2int_rn(512.f * sm.desc[lane * 4 + j]);
+            packed |= (unsigned)min(max(q, 0), 255) << (8 * j);
+        }
+        reinterpret_cast<unsigned*>(out128)[lane] = packed;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * EF_DESC_WARPS + warp;
+    if (i >= job.n) return;
+    const float4 k = job.kpts[i];
+    ef_hashsift_one(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)i * 128, lane);
+}
+
+void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
+{
+    if (job.n <= 0) return;
+    const size_t smem = sizeof(EfSiftSmem) * EF_DESC_WARPS;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ef_hashsift_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_DESC_WARPS), EF_DESC_WARPS * 32, smem, s>>>(job, t, sift128);
+    EF_COUNT_LAUNCH(1);
+}
+
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.y;
+    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    int level = p.first_level;
+    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].kpt_block_start) level++;
+    const EfLevel& L = p.lv[level];
+    const int i = (blockIdx.x - L.kpt_block_start) * EF_DESC_WARPS + warp;
+    if (i >= ctr[level].selected) return;
+    int offset = 0;
+    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
+    const int row = offset + i;
+    if (row >= p.nfeatures) return;
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
+    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
+    // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
+    ef_hashsift_one(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],
+                    sift128 + ((size_t)frame * p.nfeatures + row) * 128, lane);
+}
+
+void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
+{
+    if (p.total_kpt_blocks <= 0) return;
+    const size_t smem = sizeof(EfSiftSmem) * EF_DESC_WARPS;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ef_hashsift_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    ef_hashsift_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t, sift128);
+    EF_COUNT_LAUNCH(1);
+}
+
+// =================================================================================================
+// HashSIFT projection + sign + pack (hash_sift.cpp:353-378), exact: out = float32(sum_k a_k * w_k) with
+// the sum carried in double in ascending k (every product u8 x fp32 is exact in double).
+// weights_t: 129 x nbits (transposed at create).  16 keypoints per CTA, one output bit column per thread.
+// =================================================================================================
+#define EF_PROJ_KP 16
+__global__ void __launch_bounds__(256) ef_hashsift_project_kernel(const uint8_t* __restrict__ sift128, int n_cap, const int* __restrict__ d_n,
+                                                                  size_t frame_rows, const float* __restrict__ weights_t, int nbits,
+                                                                  uint8_t* __restrict__ desc, size_t desc_stride, int desc_pitch,
+                                                                  float* __restrict__ proj_out)
+{
+    __shared__ float s_a[EF_PROJ_KP][132];
+    const int frame = blockIdx.y;
+    const int n = d_n ? min(d_n[frame], n_cap) : n_cap;
+    const int k0 = blockIdx.x * EF_PROJ_KP;
+    if (k0 >= n) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint8_t* src = sift128 + (size_t)frame * frame_rows * 128;
+    for (int i = tid; i < EF_PROJ_KP * 129; i += 256) {
+        const int kk = i / 129, k = i - kk * 129;
+        float v = 0.f;
+        if (k0 + kk < n) v = (k == 0) ? 1.f : (float)src[(size_t)(k0 + kk) * 128 + (k - 1)];
+        s_a[kk][k] = v;
+    }
+    __syncthreads();
+    for (int j = tid; j < nbits; j += 256) {
+        double acc[EF_PROJ_KP];
+#pragma unroll
+        for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[kk] = 0.0;
+        for (int k = 0; k < 129; k++) {
+            const double wv = (double)weights_t[(size_t)k * nbits + j];
+#pragma unroll
+            for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[kk] = fma((double)s_a[kk][k], wv, acc[kk]);
+        }
+#pragma unroll
+        for (int kk = 0; kk < EF_PROJ_KP; kk++) {
+            const float tv = (float)acc[kk];
+            const bool valid = k0 + kk < n;
+            const unsigned bal = __brev(__ballot_sync(0xffffffffu, tv > 0));
+            if (valid) {
+                if (proj_out) proj_out[((size_t)frame * frame_rows + k0 + kk) * nbits + j] = tv;
+                if (lane < 4)
+                    desc[(size_t)frame * desc_stride + (size_t)(k0 + kk) * desc_pitch + ((j & ~31) >> 3) + lane] =
+                        (uint8_t)(bal >> (24 - 8 * lane));
+            }
+        }
+    }
+}
+
+void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const float* weights, int nbits,
+                                uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s)
+{
+    // single-frame form; the batched form is launched from ef_api.cu through ef_launch_hashsift_project_batch
+    if (n_cap <= 0) return;
+    ef_hashsift_project_kernel<<<dim3(ef_div_up(n_cap, EF_PROJ_KP), 1), 256, 0, s>>>(sift128, n_cap, d_n, (size_t)n_cap, weights, nbits,
+                                                                                      desc, 0, desc_pitch, proj_out);
+    EF_COUNT_LAUNCH(1);
+}
+
+void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
+                                      uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
+{
+    if (n_cap <= 0 || nframes <= 0) return;
+    ef_hashsift_project_kernel<<<dim3(ef_div_up(n_cap, EF_PROJ_KP), nframes), 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, nbits,
+                                                                                            desc, desc_stride, desc_pitch, proj_out);
+    EF_COUNT_LAUNCH(1);
+}
+
+// =================================================================================================
+// convertKeypointsKernel (cuda_efficient_features.cu:250-263): 5 x N rows -> (x, y, PATCH_SIZE, angle)
+// =================================================================================================
+__global__ void ef_convert_rows_kernel(const uint8_t* __restrict__ kpts5, size_t pitch, int n, float4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const short2 pt = reinterpret_cast<const short2*>(kpts5 + (size_t)EF_LOCATION_ROW * pitch)[i];
+    float4 k;
+    k.x = pt.x; k.y = pt.y; k.z = EF_PATCH_SIZE;
+    k.w = reinterpret_cast<const float*>(kpts5 + (size_t)EF_ANGLE_ROW * pitch)[i];
+    out[i] = k;
+}
+
+void ef_launch_convert_rows(const float* kpts5, size_t kpts_pitch, int n, float4* out, cudaStream_t s)
+{
+    if (n <= 0) return;
+    ef_convert_rows_kernel<<<ef_div_up(n, 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(kpts5), kpts_pitch, n, out);
+    EF_COUNT_LAUNCH(1);
+}

@@ -1,0 +1,164 @@
+/*
+ * ef_b200.h -- C ABI of the B200-native detectAndCompute hot path (libef_b200.so).
+ *
+ * Plain C, POD only: no OpenCV, torch or CUDA types in the signatures (streams are passed as
+ * void* holding a cudaStream_t).  Every entry point names the reference interface it replaces
+ * (fixstars/cuda-efficient-features @ 761db2b, paths relative to modules/cuda_efficient_features/).
+ *
+ * Contract
+ *   - All work is enqueued on the caller's stream; no entry point ending in _async synchronises
+ *     with the host, allocates device memory or launches on another stream.  Counts stay on the
+ *     device (the reference blocks twice per pyramid level, src/cuda_fast.cu:241-243,
+ *     src/cuda_efficient_features.cu:337-339).
+ *   - Outputs have fixed capacity: keypoints are a 5 x capacity float matrix in the reference's
+ *     row layout (include/cuda_efficient_features.h:32-37), capacity = nfeatures columns;
+ *     *d_count receives N <= nfeatures, columns [0,N) are valid.
+ *   - Returns EF_OK or an ef_status error; ef_last_error_string() describes the last failure.
+ *   - One handle per concurrent stream (the reference object is equally stateful,
+ *     src/cuda_efficient_features.cpp:391-403).  Parameters are per handle and per device: no
+ *     process-global __constant__ state (the reference's BAD tables are global, src/cuda_bad.cu:49-50).
+ *   - There is no CPU fallback: if the CUDA device or kernels are unavailable every call fails.
+ */
+#ifndef EF_B200_H
+#define EF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EF_MAX_LEVELS 16
+
+/* EfficientFeatures::DescriptorType, include/cuda_efficient_features.h:39-45 */
+typedef enum ef_desc_type { EF_BAD_256 = 0, EF_BAD_512 = 1, EF_HASH_SIFT_256 = 2, EF_HASH_SIFT_512 = 3 } ef_desc_type;
+
+/* rows of the keypoint matrix, include/cuda_efficient_features.h:32-37 */
+enum { EF_LOCATION_ROW = 0, EF_RESPONSE_ROW = 1, EF_ANGLE_ROW = 2, EF_OCTAVE_ROW = 3, EF_SIZE_ROW = 4, EF_ROWS_COUNT = 5 };
+
+typedef enum ef_status {
+    EF_OK = 0,
+    EF_ERR_BAD_ARG = 1,     /* CV_Assert / CV_Error(StsBadArg) in the reference */
+    EF_ERR_CUDA = 2,        /* CUDA runtime failure (the reference only prints these, src/cuda_macro.h:23-28) */
+    EF_ERR_CAPACITY = 3,    /* image / batch larger than the handle was created for */
+    EF_ERR_UNSUPPORTED = 4
+} ef_status;
+
+/* EfficientFeatures::create(nfeatures, scaleFactor, nlevels, firstLevel, fastThreshold, nonmaxRadius, dtype)
+ * (include/cuda_efficient_features.h:47-48) plus the capacities the workspace is planned for. */
+typedef struct ef_params {
+    int nfeatures;        /* 5000 */
+    float scale_factor;   /* 1.2f */
+    int nlevels;          /* 8    */
+    int first_level;      /* 0    */
+    int fast_threshold;   /* 20   */
+    int nonmax_radius;    /* 15   */
+    int desc_type;        /* ef_desc_type; reference default HASH_SIFT_256 */
+    float desc_scale;     /* BAD scaleFactor / HashSIFT croppingScale of the compute-only API; the
+                             detectAndCompute path always uses 1 (src/cuda_efficient_features.cpp:48-69) */
+    int max_width;        /* largest frame the workspace is planned for */
+    int max_height;
+    int max_batch;        /* frames per batched call */
+    int max_keypoints;    /* capacity of the compute-only API (>= nfeatures) */
+    int device;           /* CUDA device ordinal */
+} ef_params;
+
+typedef struct ef_handle ef_handle;
+
+void ef_default_params(ef_params* p);
+
+/* replaces EfficientFeatures::create / EfficientFeaturesImpl ctor (src/cuda_efficient_features.cpp:188-195,406-411);
+ * allocates the whole workspace once (the reference grows DeviceBuffers lazily, src/device_buffer.cpp:42-52). */
+int ef_create(const ef_params* params, ef_handle** out);
+void ef_destroy(ef_handle* h);
+
+/* the 7 setter/getter pairs, include/cuda_efficient_features.h:78-97.  Capacities cannot change. */
+typedef enum ef_param_id {
+    EF_PARAM_MAX_FEATURES = 0, EF_PARAM_SCALE_FACTOR = 1, EF_PARAM_NLEVELS = 2, EF_PARAM_FIRST_LEVEL = 3,
+    EF_PARAM_FAST_THRESHOLD = 4, EF_PARAM_NONMAX_RADIUS = 5, EF_PARAM_DESCRIPTOR_TYPE = 6, EF_PARAM_DESC_SCALE = 7
+} ef_param_id;
+int ef_set_param(ef_handle* h, int id, double value);
+int ef_get_param(const ef_handle* h, int id, double* value);
+
+size_t ef_workspace_bytes(const ef_handle* h);
+int ef_descriptor_size(const ef_handle* h);            /* descriptorSize(): nbits/8, src/cuda_efficient_features.cpp:351 */
+const char* ef_last_error_string(const ef_handle* h);
+const char* ef_version(void);
+
+/* replaces EfficientFeaturesImpl::detectAndComputeAsync with GpuMat arguments
+ * (src/cuda_efficient_features.cpp:225-321); d_desc == NULL gives detectAsync (:215-218).
+ *   d_img       CV_8UC1 device image, `pitch` bytes per row
+ *   d_kpts      5 x nfeatures floats, `kpts_pitch` bytes per row (row 0 = short2, row 3 = int)
+ *   d_desc      nfeatures x descriptorSize bytes, `desc_pitch` bytes per row, or NULL
+ *   d_count     one int on the device: number of valid columns/rows */
+int ef_detect_and_compute_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                                float* d_kpts, size_t kpts_pitch, uint8_t* d_desc, size_t desc_pitch,
+                                int* d_count, void* stream);
+
+/* Batched form (new; the reference processes one frame per call): nframes <= max_batch frames of equal
+ * size.  Frame f reads d_imgs + f*img_stride and writes d_kpts + f*kpts_stride (bytes),
+ * d_desc + f*desc_stride, d_counts[f]. */
+int ef_detect_and_compute_batch_async(ef_handle* h, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
+                                      int width, int height, float* d_kpts, size_t kpts_stride, size_t kpts_pitch,
+                                      uint8_t* d_desc, size_t desc_stride, size_t desc_pitch, int* d_counts, void* stream);
+
+/* replaces EfficientDescriptorsAsync::compute with std::vector<KeyPoint> (src/cuda_bad.cpp:72-75,
+ * src/cuda_hash_sift.cpp:139-142; keypoints packed as (pt.x, pt.y, size, angle),
+ * src/cuda_efficient_features.cpp:116-128).  d_kpts_xysa: n x 4 floats on the device. */
+int ef_compute_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                     const float* d_kpts_xysa, int n, uint8_t* d_desc, size_t desc_pitch, void* stream);
+
+/* replaces EfficientFeaturesImpl::computeAsync with a 5 x N GpuMat of keypoints
+ * (src/cuda_efficient_features.cpp:220-223 -> getKeypointsMat :104-114 -> convertKeypointsKernel,
+ * src/cuda_efficient_features.cu:250-263: only LOCATION and ANGLE rows are read, size is forced to 31). */
+int ef_compute_rows_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height,
+                          const float* d_kpts5, size_t kpts_pitch, int n, uint8_t* d_desc, size_t desc_pitch, void* stream);
+
+/* replaces detectAndCompute / detect with cv::Mat arguments (src/cuda_efficient_features.cpp:197-213,
+ * upload :76, download :316-320): HOST buffers; does the H2D copy, the device pipeline and the D2H
+ * copies on `stream`, then synchronises once.  h_desc may be NULL.  *h_count = N. */
+int ef_detect_and_compute_host(ef_handle* h, const uint8_t* h_img, size_t pitch, int width, int height,
+                               float* h_kpts5, uint8_t* h_desc, int* h_count, void* stream);
+/* batched host form: frames contiguous with img_stride bytes between them; outputs nfeatures-capacity each */
+int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h_imgs, size_t img_stride, size_t pitch,
+                                     int width, int height, float* h_kpts5, uint8_t* h_desc, int* h_counts, void* stream);
+
+/* ---- introspection for stage-by-stage parity tests (not part of the reference API) ---------- */
+typedef struct ef_level_view {
+    int width, height;
+    float scale;                 /* scales_[s] */
+    int quota;                   /* nfeaturesPerLevel_[s] */
+    const uint8_t* d_image;      /* imagePyr_[s] (level 0 aliases the caller's image) */
+    size_t image_pitch;
+    const uint8_t* d_blurred;    /* blurPyr_[s] (valid after a call that computed descriptors) */
+    size_t blurred_pitch;
+    const float* d_response;     /* dense Harris map, -inf where not a FAST corner */
+    size_t response_pitch;       /* in floats */
+} ef_level_view;
+int ef_debug_level_view(const ef_handle* h, int frame, int level, ef_level_view* out);
+/* per level {corners, survivors, selected}; synchronises the stream passed */
+int ef_debug_level_counts(ef_handle* h, int frame, int* h_counts3, void* stream);
+/* HashSIFT stage outputs of the last compute call: n x 128 uint8 SIFT vector, n x nbits fp32 projection
+ * (projection only kept when ef_debug_keep_projection(h,1) was set before the call) */
+int ef_debug_keep_projection(ef_handle* h, int keep);
+int ef_debug_hashsift_views(const ef_handle* h, const uint8_t** d_sift128, const float** d_projection);
+/* blocking device->host 2-D copy of one of the views above (tests only) */
+int ef_debug_copy_to_host(ef_handle* h, void* dst, size_t dst_pitch, const void* d_src, size_t src_pitch,
+                          size_t width_bytes, size_t rows);
+
+/* ---- measurement support (bench.py) ---------------------------------------------------------- */
+/* per-stage device timing with CUDA events recorded on the caller's stream between the stages of
+ * ef_detect_and_compute*_async.  ef_stage_times() synchronises, returns the SUM of milliseconds per stage
+ * over all calls since the last enable/reset and the number of calls, and resets the accumulators. */
+enum { EF_STAGE_PYRAMID = 0, EF_STAGE_SCORE = 1, EF_STAGE_NMS = 2, EF_STAGE_COMPACT = 3, EF_STAGE_SELECT = 4,
+       EF_STAGE_ANGLE_PACK = 5, EF_STAGE_BLUR = 6, EF_STAGE_DESCRIBE = 7, EF_STAGE_PROJECT = 8, EF_NUM_STAGES = 9 };
+int ef_stage_timing_enable(ef_handle* h, int enable);
+int ef_stage_times(ef_handle* h, float* ms_sum /* [EF_NUM_STAGES] */, int* ncalls);
+/* number of kernels this library has launched in the process so far */
+unsigned long long ef_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EF_B200_H */
