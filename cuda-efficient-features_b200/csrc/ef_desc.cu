@@ -8,6 +8,7 @@
 // Compiled with -fmad=false: the CPU reference is a generic x86-64 build without FMA, so every
 // a*b+c below must stay two roundings.
 #include "ef_common.cuh"
+#include "ef_libm_f32.cuh"
 
 #include <cfloat>
 
@@ -342,9 +343,9 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const float PI_1_0F = 3.14159274f;
         const float s = croppingScale * size / (0.5f * (float)(32 + 32));
         const float theta = PI_1_0F * angle / 180;
-        // cosf/sinf: evaluated in double and rounded once (DESIGN.md "transcendentals")
-        const float cost = s * (angle >= 0 ? (float)cos((double)theta) : 1.f);
-        const float sint = s * (angle >= 0 ? (float)sin((double)theta) : 0.f);
+        // cosf/sinf: the host libm's algorithm, bit for bit (ef_libm_f32.cuh)
+        const float cost = s * (angle >= 0 ? ef_libm::cosf_glibc(theta) : 1.f);
+        const float sint = s * (angle >= 0 ? ef_libm::sinf_glibc(theta) : 0.f);
         const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
         const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
         const int x = lane;

@@ -1,0 +1,144 @@
+"""CPU-only tests: the oracle against the reference build (oracle/_ref), the committed golden vectors and
+size-independent properties; host-side geometry."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+# ---- geometry: SURVEY.md section 8 table (probe of cuda_efficient_features.cpp:144-155,164-173) ---------------
+def test_level_geometry_and_quotas(oracle):
+    ws, hs, sc = oracle.level_geometry(3840, 2160)
+    assert ws == [3840, 3200, 2667, 2222, 1852, 1543, 1286, 1072]
+    assert hs == [2160, 1800, 1500, 1250, 1042, 868, 723, 603]
+    ws, hs, _ = oracle.level_geometry(1920, 1080)
+    assert ws == [1920, 1600, 1333, 1111, 926, 772, 643, 536] and hs == [1080, 900, 750, 625, 521, 434, 362, 301]
+    ws, hs, _ = oracle.level_geometry(7680, 4320)
+    assert ws == [7680, 6400, 5333, 4444, 3704, 3086, 2572, 2143] and hs == [4320, 3600, 3000, 2500, 2083, 1736, 1447, 1206]
+    assert [f"{float(s):.6f}" for s in sc] == ["1.000000", "1.200000", "1.440000", "1.728000", "2.073600", "2.488320", "2.985985", "3.583182"]
+    assert oracle.level_quotas(5000) == [1086, 905, 754, 628, 524, 436, 364, 303]
+    assert oracle.level_quotas(40000) == [8687, 7239, 6033, 5027, 4189, 3491, 2909, 2425]
+
+
+# ---- descriptors: golden vectors generated from the reference's own bad.cpp / hash_sift.cpp -------------------
+def test_descriptors_match_reference_golden(oracle):
+    g = np.load(GOLD / "desc_golden.npz")
+    img, k = g["image"], g["keypoints"]
+    for nbits in (256, 512):
+        for scale in (1, 5):
+            assert np.array_equal(oracle.bad(img, k, float(scale), nbits), g[f"bad{nbits}_s{scale}"]), (nbits, scale)
+        assert np.array_equal(oracle.hashsift(img, k, 1.0, nbits), g[f"hashsift{nbits}"]), nbits
+    assert np.array_equal(oracle.hashsift_features(img, k, 1.0).view(np.uint32), g["hashsift_features"].view(np.uint32))
+
+
+def test_descriptors_match_reference_build(oracle, reference):
+    """live comparison with oracle/_ref (the unmodified reference sources) on noise and on a stress set"""
+    import efo
+    for (w, h, seed) in ((640, 480, 1), (333, 257, 2)):
+        img = oracle.synth_frame(util.SEED + seed, 0, w, h)
+        k = efo.stress_keypoints(w, h, 3000, seed=seed)
+        for nbits in (256, 512):
+            assert np.array_equal(oracle.bad(img, k, 1.0, nbits), reference.bad(img, k, 1.0, nbits))
+            assert np.array_equal(oracle.bad(img, k, 6.75, nbits), reference.bad(img, k, 6.75, nbits))
+            assert np.array_equal(oracle.hashsift(img, k, 1.0, nbits), reference.hashsift(img, k, 1.0, nbits))
+        assert np.array_equal(oracle.hashsift_features(img, k, 1.0), reference.hashsift_features(img, k, 1.0))
+
+
+def test_reference_jpeg_protocol(oracle, reference):
+    """the reference's own test protocol (tests/descriptor_test.cpp:19-75): its 11 JPEGs, detector keypoints,
+    CPU descriptors.  Here: oracle == reference build, 0 differing bytes (bar: 2e-5 / 1e-4)."""
+    cv2 = pytest.importorskip("cv2")
+    p = Path("/root/reference/tests/data/images/100_7103.JPG")
+    if not p.exists():
+        pytest.skip("reference test images absent")
+    import efo
+    img = cv2.imread(str(p), cv2.IMREAD_GRAYSCALE)[::2, ::2].copy()
+    kp, _ = oracle.detect(img, oracle.make_params(nfeatures=3000, desc_type=efo.BAD_256))
+    k = np.stack([kp["x"], kp["y"], kp["size"], kp["angle"]], axis=1).astype(np.float32)
+    assert len(k) > 1000
+    for nbits in (256, 512):
+        assert np.array_equal(oracle.bad(img, k, 1.0, nbits), reference.bad(img, k, 1.0, nbits))
+        assert np.array_equal(oracle.hashsift(img, k, 1.0, nbits), reference.hashsift(img, k, 1.0, nbits))
+
+
+# ---- detector: golden (oracle regression pin) + properties ----------------------------------------------------
+def test_detector_golden(oracle):
+    import efo
+    g = np.load(GOLD / "detect_golden.npz")
+    img = oracle.synth_frame(int(g["seed"]), 0, int(g["width"]), int(g["height"]))
+    assert int(img.astype(np.uint64).sum()) == int(g["image_checksum"])
+    kp, desc, counts = oracle.detect_and_compute(img, oracle.make_params(nfeatures=int(g["nfeatures"]), desc_type=efo.BAD_256))
+    assert np.array_equal(counts, g["counts"])
+    assert kp.tobytes() == g["keypoints"].tobytes()
+    assert np.array_equal(desc, g["descriptors"])
+
+
+def _arc9_bruteforce(bits):
+    return any(all(bits[(s + j) % 16] for j in range(9)) for s in range(16))
+
+
+def test_fast_predicate_bruteforce(oracle):
+    """cuda_fast.cu:162-166 LUT == '>= 9 contiguous ring pixels all darker or all brighter'"""
+    rng = np.random.default_rng(3)
+    dy = [3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3]
+    dx = [0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1]
+    for _ in range(3000):
+        img = rng.integers(0, 256, (7, 7), dtype=np.uint8)
+        if rng.random() < 0.5:   # make arcs likely
+            img[:] = rng.integers(60, 200)
+            start, ln = rng.integers(0, 16), rng.integers(7, 12)
+            for j in range(ln):
+                img[3 + dy[(start + j) % 16], 3 + dx[(start + j) % 16]] = int(img[3, 3]) + (25 if rng.random() < 0.5 else 21) * (1 if start % 2 else -1)
+        v, th = int(img[3, 3]), 20
+        ring = [int(img[3 + dy[k], 3 + dx[k]]) for k in range(16)]
+        want = _arc9_bruteforce([q < v - th for q in ring]) or _arc9_bruteforce([q > v + th for q in ring])
+        assert oracle.fast_is_corner(img, 3, 3, th) == want
+
+
+def test_nms_properties(oracle):
+    img = oracle.synth_frame(util.SEED + 9, 0, 400, 300)
+    resp, n = oracle.score_map(img, 20)
+    assert n > 1000 and np.isfinite(resp[:15]).sum() == 0 and np.isfinite(resp[:, :15]).sum() == 0
+    xs, ys, rs = oracle.radius_nms(resp, 15)
+    pts = np.stack([xs, ys], 1).astype(np.int64)
+    d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, 10 ** 9)
+    assert d2.min() >= 225                      # survivors are pairwise >= r apart
+    order = np.lexsort((xs, ys))
+    assert np.array_equal(order, np.arange(len(xs)))   # raster order
+    # idempotence: NMS of the survivor-only map keeps everything
+    sparse = np.full_like(resp, -np.inf)
+    sparse[ys, xs] = rs
+    xs2, ys2, _ = oracle.radius_nms(sparse, 15)
+    assert np.array_equal(xs, xs2) and np.array_equal(ys, ys2)
+    # radius 0 keeps every corner
+    xs0, _, _ = oracle.radius_nms(resp, 0)
+    assert len(xs0) == n
+
+
+def test_blur_and_resize_properties(oracle):
+    flat = np.full((64, 80), 137, np.uint8)
+    assert np.array_equal(oracle.gaussian_blur7(flat), flat)
+    img = oracle.synth_frame(util.SEED + 10, 0, 96, 64)
+    assert np.array_equal(oracle.resize_linear(img, 96, 64), img)          # ratio 1: identity
+    b = oracle.gaussian_blur7(img)
+    ref = np.pad(img.astype(np.float64), 3, mode="reflect")                 # BORDER_REFLECT_101
+    taps = np.array([0.07015932, 0.13107488, 0.19071282, 0.21610594, 0.19071282, 0.13107488, 0.07015932])
+    acc = sum(taps[i] * taps[j] * ref[i:i + 64, j:j + 96] for i in range(7) for j in range(7))
+    assert np.abs(b.astype(np.float64) - acc).max() <= 0.51                 # u8 rounding of the exact 7x7 Gaussian
+    empty_kp = np.zeros((0, 4), np.float32)
+    assert oracle.bad(img, empty_kp, 1.0, 256).shape == (0, 32)
+
+
+def test_detect_counts_scale(oracle):
+    """delivered keypoints on noise follow the survey's workload estimate (~1 survivor / 800 px)"""
+    import efo
+    img = oracle.synth_frame(util.SEED + 1, 0, 1920, 1080)
+    kp, counts = oracle.detect(img, oracle.make_params(nfeatures=5000, desc_type=efo.BAD_256))
+    assert 4500 <= len(kp) <= 5000
+    assert abs(counts[0, 0] / (1890 * 1050) - 0.25) < 0.02
+    assert (kp["octave"][1:] >= kp["octave"][:-1]).all()
