@@ -72,7 +72,7 @@ struct ef_handle {
 
     uint8_t* d_ws = nullptr;
     EfLevelCounters* d_counters = nullptr;
-    short2* d_nms_offsets = nullptr;
+    int* d_nms_offsets = nullptr;
     int nms_noffsets = 0, nms_R = 0, nms_r2 = 0, nms_stage_end[4] = { 0, 0, 0, 0 };
     int nms_radius_built = -1;
 
@@ -190,7 +190,8 @@ int build_nms_offsets(ef_handle* h)
     const int r2 = (int)std::ceil(rf * rf);
     int R = 0;
     while ((R + 1) * (R + 1) < r2) R++;
-    std::vector<short2> offs;
+    std::vector<int> offs;
+    const int SW = EF_TILE + 2 * R;
     int stage_end[4] = { 0, 0, 0, 0 };
     const int ring_limit[4] = { 1, 3, 7, 1 << 30 };
     int prev = 0;
@@ -198,12 +199,12 @@ int build_nms_offsets(ef_handle* h)
         for (int ring = prev + 1; ring <= std::min(ring_limit[st], R); ring++)
             for (int dy = -ring; dy <= ring; dy++)
                 for (int dx = -ring; dx <= ring; dx++)
-                    if (std::max(std::abs(dx), std::abs(dy)) == ring && dx * dx + dy * dy < r2) offs.push_back(make_short2((short)dx, (short)dy));
+                    if (std::max(std::abs(dx), std::abs(dy)) == ring && dx * dx + dy * dy < r2) offs.push_back(dy * SW + dx);
         stage_end[st] = (int)offs.size();
         prev = std::min(ring_limit[st], R);
     }
     if (!offs.empty())
-        EF_CUDA(h, cudaMemcpy(h->d_nms_offsets, offs.data(), offs.size() * sizeof(short2), cudaMemcpyHostToDevice));
+        EF_CUDA(h, cudaMemcpy(h->d_nms_offsets, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->nms_noffsets = (int)offs.size();
     h->nms_R = R; h->nms_r2 = r2;
     std::memcpy(h->nms_stage_end, stage_end, sizeof(stage_end));
@@ -271,7 +272,7 @@ int allocate(ef_handle* h)
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { total += bytes; return cudaMalloc(ptr, bytes ? bytes : 1); };
     EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
     EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
-    EF_CUDA(h, alloc((void**)&h->d_nms_offsets, sizeof(short2) * 129 * 129));
+    EF_CUDA(h, alloc((void**)&h->d_nms_offsets, sizeof(int) * 129 * 129));
     h->sift_rows = std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
     EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
     EF_CUDA(h, alloc((void**)&h->d_integral, (size_t)(p.max_width + 1) * (p.max_height + 1) * 4));

@@ -56,7 +56,7 @@ struct EfPipe {
     // workspace
     uint8_t* ws; unsigned long long ws_stride;           // per-frame slot
     EfLevelCounters* counters; /* [frame][EF_MAX_LEVELS] */
-    const short2* nms_offsets;                            // disc offsets sorted by Chebyshev ring
+    const int* nms_offsets;                               // disc offsets (dy*SW+dx in the NMS smem tile) sorted by Chebyshev ring
     int nms_stage_end[4];                                 // offsets [0,e0) ring<=1, [e0,e1) ring<=3, [e1,e2) ring<=7, rest
     EfLevel lv[EF_MAX_LEVELS];
 };

@@ -299,16 +299,25 @@ void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
 
 // =================================================================================================
 // HashSIFT features: rectified 32x32 patch -> deterministic 4x4x8 gradient histogram -> 128 u8
+//
+// One HALF-WARP per keypoint (2 keypoints per warp, 8 per 128-thread CTA).  In the histogram phase lane c of
+// the half-warp owns histogram cell c (4x4 cells) and walks the <= 16x16 pixels that feed it in raster
+// order, adding the two orientation shares into ITS OWN 10 accumulators in shared memory (dynamic bin
+// index, no atomics, no cross-lane sharing): every accumulator receives exactly the CPU's sequence of
+// additions (hash_sift.cpp:233-290), so the 128-vector is bit-identical, unlike the reference GPU kernel's
+// shared-memory float atomics (cuda_hash_sift.cu:282-289).
 // =================================================================================================
-struct EfSiftSmem {
-    float bf[32];      // fractional row/col bin of patch row r = y+1 (index y), hash_sift.cpp:179-191
-    int bi[32];        // integer bin
-    float mag[900];
-    float of[900];
+#define EF_SIFT_KP_PER_CTA 8
+#define EF_SIFT_PIX 912   // 30x30 gradient pixels stored at y*30 + x + 2*(y>>3): the skew spreads the 16 cells over 16 banks
+struct EfSiftSmem {       // per keypoint
+    float mag[EF_SIFT_PIX];
+    float of[EF_SIFT_PIX];
+    float hist[16 * 11];  // [cell][bin 0..9], pitch 11
     float desc[128];
     uint8_t patch[32 * 32];
-    uint8_t oi[904];
+    uint8_t oi[EF_SIFT_PIX];
 };
+struct EfSiftBins { float bf[32]; int bi[32]; }; // per CTA: bin of patch row/col r = y+1 (index y)
 
 // hist row/col bin of patch row r = y+1 (hash_sift.cpp:179-180,186-191): scale * (r - 16) + 1.5, scale = 1/8
 __device__ __forceinline__ void ef_sift_bin(int r, int& bi, float& bf)
@@ -321,23 +330,25 @@ __device__ __forceinline__ void ef_sift_bin(int r, int& bi, float& bf)
     bf = b - (float)bi;
 }
 
-// normalize(), hash_sift.cpp:150-160: sequential sum, every lane computes it redundantly
-__device__ __forceinline__ void ef_sift_normalize(float* d, int lane)
+// normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
+__device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
 {
     float sum = 0.f;
+#pragma unroll 8
     for (int i = 0; i < 128; i++) { const float v = d[i]; sum += v * v; }
     const float nrm = fmaxf(sqrtf(sum), FLT_EPSILON);
     const float scale = 1.f / nrm;
     __syncwarp();
-    for (int i = lane; i < 128; i += 32) d[i] *= scale;
+    for (int i = hl; i < 128; i += 16) d[i] *= scale;
     __syncwarp();
 }
 
+// All 32 lanes call this; lanes 0-15 work on one keypoint, lanes 16-31 on another (sm, kx.. differ per half).
 __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
                                                 float kx, float ky, float size, float angle, float croppingScale,
-                                                const EfHashSiftTables& t, EfSiftSmem& sm, uint8_t* out128, int lane)
+                                                const EfHashSiftTables& t, EfSiftSmem& sm, const EfSiftBins& bins,
+                                                uint8_t* out128, bool store, int hl)
 {
-    if (lane < 30) { int bi; float bf; ef_sift_bin(lane + 1, bi, bf); sm.bi[lane] = bi; sm.bf[lane] = bf; }
     // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
     {
         const float PI_1_0F = 3.14159274f;
@@ -348,178 +359,186 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const float sint = s * (angle >= 0 ? ef_libm::sinf_glibc(theta) : 0.f);
         const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
         const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
-        const int x = lane;
         for (int y = 0; y < 32; y++) {
-            const float u = M00 * (float)x + M01 * (float)y + M02;
-            const float v = M10 * (float)x + M11 * (float)y + M12;
-            uint8_t dstVal = 0;
-            const int ui = (int)floorf(u);
-            const int vi = (int)floorf(v);
-            if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
-                const uint8_t* q = img + (size_t)vi * pitch + ui;
-                const float du = u - (float)ui;
-                const float dv = v - (float)vi;
-                const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
-                const float tmp1 = (1 - du) * (float)q[pitch] + du * (float)q[pitch + 1];
-                const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
-                dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
+#pragma unroll
+            for (int xx = 0; xx < 2; xx++) {
+                const int x = hl + 16 * xx;
+                const float u = M00 * (float)x + M01 * (float)y + M02;
+                const float v = M10 * (float)x + M11 * (float)y + M12;
+                uint8_t dstVal = 0;
+                const int ui = (int)floorf(u);
+                const int vi = (int)floorf(v);
+                if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
+                    const uint8_t* q = img + (size_t)vi * pitch + ui;
+                    const float du = u - (float)ui;
+                    const float dv = v - (float)vi;
+                    const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
+                    const float tmp1 = (1 - du) * (float)q[pitch] + du * (float)q[pitch + 1];
+                    const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
+                    dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
+                }
+                sm.patch[y * 32 + x] = dstVal;
             }
-            sm.patch[y * 32 + x] = dstVal;
         }
     }
+    for (int j = hl; j < 16 * 11; j += 16) sm.hist[j] = 0.f;
     __syncwarp();
     // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260). expf over the 30x30 positions and
     //      atan2f over dy,dx in [-255,255] are finite-domain tables (see ef_api.cu)
     {
         const float PI_2_0F = 6.28318548f;
         const float scaleO = 8 / PI_2_0F;
-        for (int i = lane; i < 900; i += 32) {
+        for (int i = hl; i < 900; i += 16) {
             const int y = i / 30, x = i - y * 30;
             const int dxi = (int)sm.patch[(y + 1) * 32 + x + 2] - (int)sm.patch[(y + 1) * 32 + x];
             const int dyi = (int)sm.patch[y * 32 + x + 1] - (int)sm.patch[(y + 2) * 32 + x + 1];
             const float dx = (float)dxi, dy = (float)dyi;
-            const float mag = t.exp_table[i] * sqrtf(dx * dx + dy * dy);
-            const float ori = t.atan2_table[(dyi + 255) * 511 + (dxi + 255)];
+            const float mag = __ldg(t.exp_table + i) * sqrtf(dx * dx + dy * dy);
+            const float ori = __ldg(t.atan2_table + (dyi + 255) * 511 + (dxi + 255));
             const float ob = scaleO * ori;
             int oi = (int)floorf(ob);
             const float of = ob - (float)oi;
             if (oi < 0) oi += 8;
             if (oi >= 8) oi -= 8;
-            sm.mag[i] = mag;
-            sm.of[i] = of;
-            sm.oi[i] = (uint8_t)oi;
+            const int idx = i + 2 * (y >> 3);
+            sm.mag[idx] = mag;
+            sm.of[idx] = of;
+            sm.oi[idx] = (uint8_t)oi;
         }
     }
     __syncwarp();
-    // ---- trilinear histogram (hash_sift.cpp:233-290).  lane = (cell, half): cell = hist (rb, cb) in 1..4,
-    //      half 0 owns orientation bins 0..4, half 1 bins 5..8.  Each accumulator receives its
-    //      contributions in raster order of the pixels, exactly like the scalar CPU loop.
+    // ---- trilinear histogram (hash_sift.cpp:233-290): lane = cell (rb, cb) in 1..4.  scale is exactly 1/8, so
+    //      bin(r) = (r-16)/8 + 1.5 and the patch rows feeding hist row rb are r in [8rb-12, 8rb+3] (clipped to
+    //      1..30); the table lookups keep the float expression authoritative for membership and weights.
     {
-        const int cell = lane >> 1, half = lane & 1;
-        const int rb = (cell >> 2) + 1, cb = (cell & 3) + 1;
-        const int b0 = half ? 5 : 0;
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
-        // rows r = y+1 in 1..30 whose bin pair (ri+1, ri+2) contains rb:  ri in {rb-2, rb-1}
-        // scale is exactly 1/8, so bin(r) = (r-16)/8 + 1.5 and the rows feeding hist row rb are
-        // r in [8rb-12, 8rb+3] (clipped to 1..30); the table lookups keep the float expression authoritative.
-        const int ylo = max(8 * rb - 12, 1) - 1, yhi = min(8 * rb + 3, 30) - 1;
-        const int xlo = max(8 * cb - 12, 1) - 1, xhi = min(8 * cb + 3, 30) - 1;
-        for (int y = ylo; y <= yhi; y++) {
-            const int ri = sm.bi[y]; const float rf = sm.bf[y];
+        const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
+        const int ybase = 8 * rb - 13, xbase = 8 * cb - 13; // pixel index y = r - 1
+        float* hc = sm.hist + hl * 11;
+        for (int iy = 0; iy < 16; iy++) {
+            const int y = ybase + iy;
+            if (y < 0 || y >= 30) continue;
+            const int ri = bins.bi[y]; const float rf = bins.bf[y];
             if (ri + 1 != rb && ri + 2 != rb) continue;
             const bool r_hi = (ri + 2 == rb);
-            for (int x = xlo; x <= xhi; x++) {
-                const int ci = sm.bi[x]; const float cf = sm.bf[x];
+            const int rowidx = y * 30 + 2 * (y >> 3);
+            for (int ix = 0; ix < 16; ix++) {
+                const int x = xbase + ix;
+                if (x < 0 || x >= 30) continue;
+                const int ci = bins.bi[x]; const float cf = bins.bf[x];
                 if (ci + 1 != cb && ci + 2 != cb) continue;
                 const bool c_hi = (ci + 2 == cb);
-                const int i = y * 30 + x;
-                const float mag = sm.mag[i];
-                const float of = sm.of[i];
-                const int oi = sm.oi[i];
+                const int idx = rowidx + x;
+                const float mag = sm.mag[idx];
+                const float of = sm.of[idx];
+                const int oi = sm.oi[idx];
                 // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
                 const float v1 = rf * mag, v0 = mag - v1;
                 const float vr = r_hi ? v1 : v0;
                 const float vc1 = cf * vr, vc0 = vr - vc1;
                 const float vc = c_hi ? vc1 : vc0;
                 const float vo1 = of * vc, vo0 = vc - vo1;
-                const int k = oi - b0; // bin oi gets vo0, bin oi+1 gets vo1
-                acc0 += (k == 0) ? vo0 : ((k == -1) ? vo1 : 0.f);
-                acc1 += (k == 1) ? vo0 : ((k == 0) ? vo1 : 0.f);
-                acc2 += (k == 2) ? vo0 : ((k == 1) ? vo1 : 0.f);
-                acc3 += (k == 3) ? vo0 : ((k == 2) ? vo1 : 0.f);
-                acc4 += (k == 4) ? vo0 : ((k == 3) ? vo1 : 0.f);
+                hc[oi] += vo0;
+                hc[oi + 1] += vo1;
             }
         }
-        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: oi <= 7)
-        const float bin8 = __shfl_sync(0xffffffffu, acc3, lane | 1); // half 1: acc3 = bin 8
-        const int e = ((rb - 1) * 4 + (cb - 1)) * 8;
-        if (half == 0) {
-            sm.desc[e + 0] = acc0 + bin8;
-            sm.desc[e + 1] = acc1;
-            sm.desc[e + 2] = acc2;
-            sm.desc[e + 3] = acc3;
-            sm.desc[e + 4] = acc4;
-        } else {
-            sm.desc[e + 5] = acc0;
-            sm.desc[e + 6] = acc1;
-            sm.desc[e + 7] = acc2;
-        }
+        __syncwarp();
+        // circular fold (hash_sift.cpp:299-302): bin0 += bin8, bin1 += bin9 (bin 9 is never written: oi <= 7)
+        float* d = sm.desc + hl * 8;
+        d[0] = hc[0] + hc[8];
+        d[1] = hc[1] + hc[9];
+#pragma unroll
+        for (int k = 2; k < 8; k++) d[k] = hc[k];
     }
     __syncwarp();
     // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
-    ef_sift_normalize(sm.desc, lane);
-    for (int i = lane; i < 128; i += 32) sm.desc[i] = fminf(sm.desc[i], 0.2f);
+    ef_sift_normalize(sm.desc, hl);
+    for (int i = hl; i < 128; i += 16) sm.desc[i] = fminf(sm.desc[i], 0.2f);
     __syncwarp();
-    ef_sift_normalize(sm.desc, lane);
+    ef_sift_normalize(sm.desc, hl);
     {
-        unsigned packed = 0;
+        unsigned packed[2] = { 0, 0 };
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int q = __float2int_rn(512.f * sm.desc[lane * 4 + j]);
-            packed |= (unsigned)min(max(q, 0), 255) << (8 * j);
+        for (int j = 0; j < 8; j++) {
+            const int q = __float2int_rn(512.f * sm.desc[hl * 8 + j]);
+            packed[j >> 2] |= (unsigned)min(max(q, 0), 255) << (8 * (j & 3));
         }
-        reinterpret_cast<unsigned*>(out128)[lane] = packed;
+        if (store) reinterpret_cast<uint2*>(out128)[hl] = make_uint2(packed[0], packed[1]);
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+__device__ __forceinline__ void ef_sift_init_bins(EfSiftBins& bins)
+{
+    if (threadIdx.x < 30) { int bi; float bf; ef_sift_bin((int)threadIdx.x + 1, bi, bf); bins.bi[threadIdx.x] = bi; bins.bf[threadIdx.x] = bf; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(EF_SIFT_KP_PER_CTA * 16) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ EfSiftBins bins;
     EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * EF_DESC_WARPS + warp;
-    if (i >= job.n) return;
-    const float4 k = job.kpts[i];
-    ef_hashsift_one(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)i * 128, lane);
+    ef_sift_init_bins(bins);
+    const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
+    const int first = blockIdx.x * EF_SIFT_KP_PER_CTA + (slot & ~1); // first keypoint of this warp
+    if (first >= job.n) return;
+    const int i = blockIdx.x * EF_SIFT_KP_PER_CTA + slot;
+    const bool valid = i < job.n;
+    const int ii = valid ? i : first;
+    const float4 k = job.kpts[ii];
+    ef_hashsift_one(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[slot], bins, sift128 + (size_t)ii * 128, valid, hl);
 }
 
 void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
 {
     if (job.n <= 0) return;
-    const size_t smem = sizeof(EfSiftSmem) * EF_DESC_WARPS;
+    const size_t smem = sizeof(EfSiftSmem) * EF_SIFT_KP_PER_CTA;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ef_hashsift_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_DESC_WARPS), EF_DESC_WARPS * 32, smem, s>>>(job, t, sift128);
+    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_KP_PER_CTA * 16, smem, s>>>(job, t, sift128);
     EF_COUNT_LAUNCH(1);
 }
 
-__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+__global__ void __launch_bounds__(EF_SIFT_KP_PER_CTA * 16) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ EfSiftBins bins;
     EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ef_sift_init_bins(bins);
+    const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
     const int frame = blockIdx.y;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
     int level = p.first_level;
     while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].kpt_block_start) level++;
     const EfLevel& L = p.lv[level];
-    const int i = (blockIdx.x - L.kpt_block_start) * EF_DESC_WARPS + warp;
-    if (i >= ctr[level].selected) return;
+    const int nsel = ctr[level].selected;
+    const int first = (blockIdx.x - L.kpt_block_start) * EF_SIFT_KP_PER_CTA + (slot & ~1);
+    if (first >= nsel) return;
+    const int i = (blockIdx.x - L.kpt_block_start) * EF_SIFT_KP_PER_CTA + slot;
     int offset = 0;
     for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
-    const int row = offset + i;
-    if (row >= p.nfeatures) return;
-    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
+    const bool valid = i < nsel && offset + i < p.nfeatures;
+    const int ii = valid ? i : first;
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[ii];
     const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
     // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
-    ef_hashsift_one(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],
-                    sift128 + ((size_t)frame * p.nfeatures + row) * 128, lane);
+    ef_hashsift_one(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[slot], bins,
+                    sift128 + ((size_t)frame * p.nfeatures + offset + ii) * 128, valid, hl);
 }
 
 void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
 {
     if (p.total_kpt_blocks <= 0) return;
-    const size_t smem = sizeof(EfSiftSmem) * EF_DESC_WARPS;
+    const size_t smem = sizeof(EfSiftSmem) * EF_SIFT_KP_PER_CTA;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ef_hashsift_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    ef_hashsift_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t, sift128);
+    ef_hashsift_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_SIFT_KP_PER_CTA * 16, smem, s>>>(p, t, sift128);
     EF_COUNT_LAUNCH(1);
 }
 
@@ -529,12 +548,14 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 // weights_t: 129 x nbits (transposed at create).  16 keypoints per CTA, one output bit column per thread.
 // =================================================================================================
 #define EF_PROJ_KP 16
+template <int NCOL>
 __global__ void __launch_bounds__(256) ef_hashsift_project_kernel(const uint8_t* __restrict__ sift128, int n_cap, const int* __restrict__ d_n,
-                                                                  size_t frame_rows, const float* __restrict__ weights_t, int nbits,
+                                                                  size_t frame_rows, const float* __restrict__ weights_t,
                                                                   uint8_t* __restrict__ desc, size_t desc_stride, int desc_pitch,
                                                                   float* __restrict__ proj_out)
 {
-    __shared__ float s_a[EF_PROJ_KP][132];
+    constexpr int nbits = 256 * NCOL;
+    __shared__ __align__(16) double s_a[129][EF_PROJ_KP]; // [k][keypoint]: one 16-byte broadcast load feeds 2 keypoints
     const int frame = blockIdx.y;
     const int n = d_n ? min(d_n[frame], n_cap) : n_cap;
     const int k0 = blockIdx.x * EF_PROJ_KP;
@@ -543,52 +564,70 @@ __global__ void __launch_bounds__(256) ef_hashsift_project_kernel(const uint8_t*
     const uint8_t* src = sift128 + (size_t)frame * frame_rows * 128;
     for (int i = tid; i < EF_PROJ_KP * 129; i += 256) {
         const int kk = i / 129, k = i - kk * 129;
-        float v = 0.f;
-        if (k0 + kk < n) v = (k == 0) ? 1.f : (float)src[(size_t)(k0 + kk) * 128 + (k - 1)];
-        s_a[kk][k] = v;
+        double v = 0.0;
+        if (k0 + kk < n) v = (k == 0) ? 1.0 : (double)src[(size_t)(k0 + kk) * 128 + (k - 1)];
+        s_a[k][kk] = v;
     }
     __syncthreads();
-    for (int j = tid; j < nbits; j += 256) {
-        double acc[EF_PROJ_KP];
+    double acc[NCOL][EF_PROJ_KP];
 #pragma unroll
-        for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[kk] = 0.0;
-        for (int k = 0; k < 129; k++) {
-            const double wv = (double)weights_t[(size_t)k * nbits + j];
+    for (int c = 0; c < NCOL; c++)
 #pragma unroll
-            for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[kk] = fma((double)s_a[kk][k], wv, acc[kk]);
+        for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[c][kk] = 0.0;
+    for (int k = 0; k < 129; k++) {
+        double wv[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) wv[c] = (double)__ldg(weights_t + (size_t)k * nbits + tid + 256 * c);
+#pragma unroll
+        for (int kp = 0; kp < EF_PROJ_KP; kp += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(&s_a[k][kp]);
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) {
+                acc[c][kp] = fma(a.x, wv[c], acc[c][kp]);
+                acc[c][kp + 1] = fma(a.y, wv[c], acc[c][kp + 1]);
+            }
         }
+    }
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) {
+        const int j = tid + 256 * c;
 #pragma unroll
         for (int kk = 0; kk < EF_PROJ_KP; kk++) {
-            const float tv = (float)acc[kk];
+            const float tv = (float)acc[c][kk];
             const bool valid = k0 + kk < n;
             const unsigned bal = __brev(__ballot_sync(0xffffffffu, tv > 0));
             if (valid) {
                 if (proj_out) proj_out[((size_t)frame * frame_rows + k0 + kk) * nbits + j] = tv;
                 if (lane < 4)
-                    desc[(size_t)frame * desc_stride + (size_t)(k0 + kk) * desc_pitch + ((j & ~31) >> 3) + lane] =
-                        (uint8_t)(bal >> (24 - 8 * lane));
+                    desc[(size_t)frame * desc_stride + (size_t)(k0 + kk) * desc_pitch + ((j & ~31) >> 3) + lane] = (uint8_t)(bal >> (24 - 8 * lane));
             }
         }
     }
 }
 
+static void ef_project_launch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
+                              uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
+{
+    const dim3 grid(ef_div_up(n_cap, EF_PROJ_KP), nframes);
+    if (nbits == 256)
+        ef_hashsift_project_kernel<1><<<grid, 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, desc, desc_stride, desc_pitch, proj_out);
+    else
+        ef_hashsift_project_kernel<2><<<grid, 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, desc, desc_stride, desc_pitch, proj_out);
+    EF_COUNT_LAUNCH(1);
+}
+
 void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const float* weights, int nbits,
                                 uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s)
 {
-    // single-frame form; the batched form is launched from ef_api.cu through ef_launch_hashsift_project_batch
     if (n_cap <= 0) return;
-    ef_hashsift_project_kernel<<<dim3(ef_div_up(n_cap, EF_PROJ_KP), 1), 256, 0, s>>>(sift128, n_cap, d_n, (size_t)n_cap, weights, nbits,
-                                                                                      desc, 0, desc_pitch, proj_out);
-    EF_COUNT_LAUNCH(1);
+    ef_project_launch(sift128, n_cap, d_n, 1, weights, nbits, desc, 0, desc_pitch, proj_out, s);
 }
 
 void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
                                       uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
 {
     if (n_cap <= 0 || nframes <= 0) return;
-    ef_hashsift_project_kernel<<<dim3(ef_div_up(n_cap, EF_PROJ_KP), nframes), 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, nbits,
-                                                                                            desc, desc_stride, desc_pitch, proj_out);
-    EF_COUNT_LAUNCH(1);
+    ef_project_launch(sift128, n_cap, d_counts, nframes, weights, nbits, desc, desc_stride, desc_pitch, proj_out, s);
 }
 
 // =================================================================================================

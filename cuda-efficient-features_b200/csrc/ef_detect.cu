@@ -214,25 +214,28 @@ void ef_launch_score(const EfPipe& p, cudaStream_t s)
 }
 
 // =================================================================================================
-// radius NMS on the dense map: tile + halo in shared memory, staged scan of the disc with
-// compaction of the still-alive candidates between stages.
+// radius NMS on the dense map: tile + halo in shared memory.
 //   i dies iff exists j != i with resp_i <= resp_j and dx^2+dy^2 < ceil(r^2)   (cuda_efficient_features.cu:90)
+// Two phases (ncu of the first version showed 69 % of the time at a barrier behind 5-thread-wide tails):
+//   1. one thread per pixel tests the innermost ring (Chebyshev distance 1) and the still-alive
+//      candidates are ballot-compacted into a list (kills ~2/3 of the corners on noise);
+//   2. one WARP per listed candidate scans the rest of the disc, 32 offsets per step in ring order,
+//      and stops at the first step that finds a stronger-or-equal neighbour (warp vote).
 // Output: one 32-bit survivor word per (tile,row) in tile-major order + per-row survivor counts.
 // =================================================================================================
 __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfPipe p)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ unsigned s_mask[EF_TILE];
-    __shared__ int s_cnt[2];
+    __shared__ int s_cnt;
 
     const int R = p.nms_R;
     const int SW = EF_TILE + 2 * R;
     float* s_r = reinterpret_cast<float*>(s_dyn);
-    short2* s_off = reinterpret_cast<short2*>(s_r + SW * SW);
-    unsigned short* s_listA = reinterpret_cast<unsigned short*>(s_off + ((p.nms_noffsets + 1) & ~1));
-    unsigned short* s_listB = s_listA + EF_TILE * EF_TILE;
+    int* s_off = reinterpret_cast<int*>(s_r + SW * SW);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_off + p.nms_noffsets);
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::tile_start);
     const EfLevel& L = p.lv[level];
@@ -241,75 +244,78 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
 
     if (tid < EF_TILE) s_mask[tid] = 0;
-    if (tid < 2) s_cnt[tid] = 0;
+    if (tid == 0) s_cnt = 0;
     for (int i = tid; i < p.nms_noffsets; i += 256) s_off[i] = p.nms_offsets[i];
-    for (int i = tid; i < SW * SW; i += 256) {
-        const int ly = i / SW, lx = i - ly * SW;
-        const int gy = y0 - R + ly, gx = x0 - R + lx;
-        float v = EF_NEG_INF;
-        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.w) v = resp[(size_t)gy * L.resp_pitch + gx];
-        s_r[i] = v;
+    // tile + halo: warp <-> row, lane <-> column pair (8-byte loads when the halo is even: x0-R is then even)
+    if ((R & 1) == 0) {
+        const int npair = SW >> 1;
+        for (int ly = warp; ly < SW; ly += 8) {
+            const int gy = y0 - R + ly;
+            const bool rowin = gy >= 0 && gy < L.h;
+            const float* row = resp + (size_t)gy * L.resp_pitch;
+            for (int lp = lane; lp < npair; lp += 32) {
+                const int gx = x0 - R + 2 * lp;
+                float2 v = make_float2(EF_NEG_INF, EF_NEG_INF);
+                if (rowin && gx >= 0 && gx + 1 < L.resp_pitch) {
+                    v = *reinterpret_cast<const float2*>(row + gx);
+                    if (gx + 1 >= L.w) v.y = EF_NEG_INF;
+                    if (gx >= L.w) v.x = EF_NEG_INF;
+                }
+                *reinterpret_cast<float2*>(&s_r[ly * SW + 2 * lp]) = v;
+            }
+        }
+    } else {
+        for (int ly = warp; ly < SW; ly += 8) {
+            const int gy = y0 - R + ly;
+            const bool rowin = gy >= 0 && gy < L.h;
+            for (int lx = lane; lx < SW; lx += 32) {
+                const int gx = x0 - R + lx;
+                float v = EF_NEG_INF;
+                if (rowin && gx >= 0 && gx < L.w) v = resp[(size_t)gy * L.resp_pitch + gx];
+                s_r[ly * SW + lx] = v;
+            }
+        }
     }
     __syncthreads();
 
-    // initial candidate list
+    // phase 1: innermost ring per pixel, compaction of the still-alive corners
+    const int k1 = p.nms_stage_end[0];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int py = (tid >> 5) + 8 * i, tx = lane;
-        const bool cand = s_r[(py + R) * SW + tx + R] > EF_NEG_INF;
-        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        const int py = warp + 8 * i;
+        const int c = (py + R) * SW + lane + R;
+        const float ri = s_r[c];
+        bool alive = ri > EF_NEG_INF;
+        if (alive) {
+            for (int k = 0; k < k1; k++)
+                if (ri <= s_r[c + s_off[k]]) { alive = false; break; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
         const int cnt = __popc(bal);
         int base = 0;
-        if (lane == 0 && cnt) base = atomicAdd(&s_cnt[0], cnt);
+        if (lane == 0 && cnt) base = atomicAdd(&s_cnt, cnt);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand) s_listA[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((py << 5) | tx);
+        if (alive) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((py << 5) | lane);
     }
     __syncthreads();
 
-    unsigned short* cur = s_listA;
-    unsigned short* nxt = s_listB;
-    int n = s_cnt[0];
-    int which = 0;
-    int k0 = 0;
-    for (int st = 0; st < 4 && n > 0; st++) {
-        const int k1 = p.nms_stage_end[st];
-        if (k1 <= k0) continue;
-        const int nround = (n + 255) & ~255;
-        for (int i = tid; i < nround; i += 256) {
-            bool alive = false;
-            unsigned short pos = 0;
-            if (i < n) {
-                pos = cur[i];
-                const int c = ((pos >> 5) + R) * SW + (pos & 31) + R;
-                const float ri = s_r[c];
-                alive = true;
-                for (int k = k0; k < k1; k++) {
-                    const short2 o = s_off[k];
-                    if (ri <= s_r[c + o.y * SW + o.x]) { alive = false; break; }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, alive);
-            const int cnt = __popc(bal);
-            int base = 0;
-            if (lane == 0 && cnt) base = atomicAdd(&s_cnt[which ^ 1], cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (alive) nxt[base + __popc(bal & ((1u << lane) - 1u))] = pos;
+    // phase 2: warp per candidate, 32 offsets per step, early exit on a warp vote
+    const int n = s_cnt;
+    const int noff = p.nms_noffsets;
+    for (int i = warp; i < n; i += 8) {
+        const int pos = s_list[i];
+        const int c = ((pos >> 5) + R) * SW + (pos & 31) + R;
+        const float ri = s_r[c];
+        bool alive = true;
+        for (int kb = k1; kb < noff; kb += 32) {
+            const int k = kb + lane;
+            const bool kill = k < noff && ri <= s_r[c + s_off[k]];
+            if (__any_sync(0xffffffffu, kill)) { alive = false; break; }
         }
-        __syncthreads();
-        n = s_cnt[which ^ 1];
-        __syncthreads();
-        if (tid == 0) s_cnt[which] = 0;
-        which ^= 1;
-        unsigned short* tmp = cur; cur = nxt; nxt = tmp;
-        k0 = k1;
-        __syncthreads();
-    }
-
-    for (int i = tid; i < n; i += 256) {
-        const int pos = cur[i];
-        atomicOr(&s_mask[pos >> 5], 1u << (pos & 31));
+        if (alive && lane == 0) atomicOr(&s_mask[pos >> 5], 1u << (pos & 31));
     }
     __syncthreads();
+
     if (tid < EF_TILE) {
         unsigned* mask = reinterpret_cast<unsigned*>(ef_ws(p, frame, L.mask_off));
         const unsigned word = s_mask[tid];
@@ -325,8 +331,7 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
 static size_t ef_nms_smem_bytes(const EfPipe& p)
 {
     const int SW = EF_TILE + 2 * p.nms_R;
-    return (size_t)SW * SW * sizeof(float) + (size_t)((p.nms_noffsets + 1) & ~1) * sizeof(short2) +
-           2 * EF_TILE * EF_TILE * sizeof(unsigned short);
+    return (size_t)SW * SW * sizeof(float) + (size_t)p.nms_noffsets * sizeof(int) + EF_TILE * EF_TILE * sizeof(unsigned short);
 }
 
 void ef_launch_nms(const EfPipe& p, cudaStream_t s)

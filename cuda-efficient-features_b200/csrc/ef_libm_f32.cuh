@@ -24,6 +24,14 @@
 
 namespace ef_libm {
 
+// 2/pi bits for the large-argument reduction (glibc __inv_pio4)
+#define EF_INV_PIO4_INIT { 0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, \
+                           0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, \
+                           0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041 }
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t ef_inv_pio4_dev[24] = EF_INV_PIO4_INIT;
+#endif
+
 EF_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
 
 EF_HD uint32_t f32_bits(float f)
@@ -79,9 +87,11 @@ EF_HD double reduce_fast(double x, int* np)
 
 EF_HD double reduce_large(uint32_t xi, int* np)
 {
-    const uint32_t inv_pio4[24] = { 0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
-                                    0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
-                                    0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041 };
+#if defined(__CUDA_ARCH__)
+    const uint32_t* inv_pio4 = ef_inv_pio4_dev;
+#else
+    static const uint32_t inv_pio4[24] = EF_INV_PIO4_INIT;
+#endif
     const double pi63 = 0x1.921FB54442D18p-62;
     const uint32_t* arr = &inv_pio4[(xi >> 26) & 15];
     const int shift = (xi >> 23) & 7;
