@@ -54,7 +54,25 @@ void compute_geometry(int w, int h, float scaleFactor, int nlevels, int nfeature
 int desc_bytes_of(int t) { return (t == EF_BAD_256 || t == EF_HASH_SIFT_256) ? 32 : 64; }
 bool is_bad(int t) { return t == EF_BAD_256 || t == EF_BAD_512; }
 
-struct LevelPlan { unsigned long long img_off, blur_off, resp_off, mask_off, rowcnt_off, surv_off, sel_off; int img_pitch, resp_pitch; };
+struct LevelPlan { unsigned long long img_off, blur_off, resp_off, blk_off, mask_off, rowcnt_off, surv_off, sel_off; int img_pitch, resp_pitch; };
+
+// radius NMS geometry (radiusSuppression, cuda_efficient_features.cu:291-292: imageRadius = ceil(r^2)) and the block edge b of
+// the block-maximum map: the largest of 8, 4, 2 with 2(b-1)^2 < r^2, so that a block lies inside the disc of each of its pixels.
+struct NmsGeom { int r2, R, block, K; };
+NmsGeom nms_geometry(int radius)
+{
+    NmsGeom g;
+    const float rf = (float)radius;
+    g.r2 = (int)std::ceil(rf * rf);
+    g.R = 0;
+    while ((g.R + 1) * (g.R + 1) < g.r2) g.R++;
+    g.block = 0;
+    for (int b = 8; b >= 2; b >>= 1)
+        if (2 * (b - 1) * (b - 1) < g.r2) { g.block = b; break; }
+    if (g.r2 <= 1) g.block = 0; // the disc holds only the pixel itself: nothing is suppressed
+    g.K = g.block ? (g.block - 1 + g.R) / g.block : 0;
+    return g;
+}
 
 } // namespace
 
@@ -72,15 +90,15 @@ struct ef_handle {
 
     uint8_t* d_ws = nullptr;
     EfLevelCounters* d_counters = nullptr;
-    int* d_nms_offsets = nullptr;
-    int nms_noffsets = 0, nms_R = 0, nms_r2 = 0, nms_stage_end[4] = { 0, 0, 0, 0 };
-    int nms_radius_built = -1;
 
     // descriptor tables (per handle, per device)
     uchar4* d_bad_boxes[2] = { nullptr, nullptr };
     unsigned char* d_bad_radius[2] = { nullptr, nullptr };
     float* d_bad_thr[2] = { nullptr, nullptr };
-    float* d_hs_weights_t[2] = { nullptr, nullptr }; // 129 x nbits (transposed)
+    float* d_hs_weights_t[2] = { nullptr, nullptr }; // 129 x nbits (transposed; fp64 fallback projection)
+    uint4* d_hs_bfrag[2] = { nullptr, nullptr };     // fixed-point digits of the projection in mma fragment order (ef_project.cu)
+    long long* d_hs_bias[2] = { nullptr, nullptr };  // column 0 of the projection as fixed-point integers
+    int hs_shift[2] = { 0, 0 };                      // fixed-point scale 2^-shift; bfrag == nullptr: table does not fit 6 digits
     float* d_exp_table = nullptr;
     float* d_atan2_table = nullptr;
 
@@ -130,8 +148,8 @@ int fail(ef_handle* h, int code, const std::string& msg)
 
 void free_all(ef_handle* h)
 {
-    cudaFree(h->d_ws); cudaFree(h->d_counters); cudaFree(h->d_nms_offsets);
-    for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); }
+    cudaFree(h->d_ws); cudaFree(h->d_counters);
+    for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); cudaFree(h->d_hs_bfrag[i]); cudaFree(h->d_hs_bias[i]); }
     cudaFree(h->d_exp_table); cudaFree(h->d_atan2_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
     cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
     cudaFree(h->d_in); cudaFree(h->d_out_kpts); cudaFree(h->d_out_desc); cudaFree(h->d_out_counts);
@@ -172,6 +190,8 @@ void plan_workspace(ef_handle* h)
         q.img_off = off; if (l > 0) off += ef_align_up(img_bytes, 256);
         q.blur_off = off; off += ef_align_up(img_bytes, 256);
         q.resp_off = off; off += ef_align_up((unsigned long long)q.resp_pitch * hh * 4, 256);
+        const int nb = nms_geometry(p.nonmax_radius).block;
+        q.blk_off = off; if (nb) off += ef_align_up((unsigned long long)ef_div_up(w, nb) * ef_div_up(hh, nb) * sizeof(EfBlockMax), 256);
         const unsigned long long tiles = (unsigned long long)ef_div_up(w, EF_TILE) * ef_div_up(hh, EF_TILE);
         q.mask_off = off; off += ef_align_up(tiles * EF_TILE * 4, 256);
         const unsigned long long surv_cap = (unsigned long long)std::max(1l, lrint(0.1 * (double)w * hh));
@@ -179,37 +199,6 @@ void plan_workspace(ef_handle* h)
         q.sel_off = off; off += ef_align_up((unsigned long long)p.nfeatures * sizeof(EfSelected), 256);
     }
     h->slot_bytes = ef_align_up(off, 4096);
-}
-
-// disc offsets (dx^2+dy^2 < r^2, excluding 0) sorted by Chebyshev ring; radiusSuppression :291-292
-int build_nms_offsets(ef_handle* h)
-{
-    const int radius = h->prm.nonmax_radius;
-    if (h->nms_radius_built == radius) return EF_OK;
-    const float rf = (float)radius;
-    const int r2 = (int)std::ceil(rf * rf);
-    int R = 0;
-    while ((R + 1) * (R + 1) < r2) R++;
-    std::vector<int> offs;
-    const int SW = EF_TILE + 2 * R;
-    int stage_end[4] = { 0, 0, 0, 0 };
-    const int ring_limit[4] = { 1, 3, 7, 1 << 30 };
-    int prev = 0;
-    for (int st = 0; st < 4; st++) {
-        for (int ring = prev + 1; ring <= std::min(ring_limit[st], R); ring++)
-            for (int dy = -ring; dy <= ring; dy++)
-                for (int dx = -ring; dx <= ring; dx++)
-                    if (std::max(std::abs(dx), std::abs(dy)) == ring && dx * dx + dy * dy < r2) offs.push_back(dy * SW + dx);
-        stage_end[st] = (int)offs.size();
-        prev = std::min(ring_limit[st], R);
-    }
-    if (!offs.empty())
-        EF_CUDA(h, cudaMemcpy(h->d_nms_offsets, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    h->nms_noffsets = (int)offs.size();
-    h->nms_R = R; h->nms_r2 = r2;
-    std::memcpy(h->nms_stage_end, stage_end, sizeof(stage_end));
-    h->nms_radius_built = radius;
-    return EF_OK;
 }
 
 int upload_tables(ef_handle* h)
@@ -237,6 +226,68 @@ int upload_tables(ef_handle* h)
             for (int k = 0; k < 129; k++) wt[(size_t)k * nbits + j] = wb[(size_t)j * 129 + k];
         EF_CUDA(h, cudaMalloc(&h->d_hs_weights_t[v], wt.size() * sizeof(float)));
         EF_CUDA(h, cudaMemcpy(h->d_hs_weights_t[v], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // exact fixed-point form for the integer tensor cores (ef_project.cu): every fp32 weight is m * 2^(e-23);
+        // S = -(smallest exponent of a lowest set bit) makes all of them integers W = w * 2^S, split into 6 balanced
+        // base-256 digits.  Falls back to the fp64 kernel if some |W| needs more than 6 digits.
+        {
+            int min_lsb = 1 << 30;
+            for (size_t i = 0; i < (size_t)nbits * 129; i++) {
+                float f; std::memcpy(&f, &wb[i], 4);
+                if (f == 0.f) continue;
+                int e; const double m = std::frexp((double)f, &e);           // f = m * 2^e, 0.5 <= |m| < 1
+                long long mant = (long long)std::ldexp(std::fabs(m), 24);   // 24-bit integer mantissa
+                int tz = 0; while (!(mant & 1)) { mant >>= 1; tz++; }
+                min_lsb = std::min(min_lsb, e - 24 + tz);
+            }
+            const int S = -min_lsb;
+            bool ok = S > 0 && S < 100;
+            std::vector<long long> W((size_t)nbits * 129);
+            for (size_t i = 0; ok && i < W.size(); i++) {
+                float f; std::memcpy(&f, &wb[i], 4);
+                const double scaled = std::ldexp((double)f, S);             // exact: power-of-two scaling of a 24-bit mantissa
+                if (std::fabs(scaled) >= 9.0e15) { ok = false; break; }
+                W[i] = (long long)scaled;
+                if ((double)W[i] != scaled) ok = false;
+            }
+            std::vector<signed char> dig; std::vector<long long> bias(nbits);
+            if (ok) {
+                dig.assign((size_t)6 * nbits * 128, 0);
+                for (int j = 0; ok && j < nbits; j++) {
+                    bias[j] = W[(size_t)j * 129];
+                    for (int k = 0; k < 128; k++) {
+                        long long x = W[(size_t)j * 129 + 1 + k];
+                        for (int d = 0; d < 6; d++) {
+                            const long long r = ((x + 128) & 255) - 128;     // balanced digit in [-128, 127]
+                            dig[((size_t)d * nbits + j) * 128 + k] = (signed char)r;
+                            x = (x - r) / 256;
+                        }
+                        if (x != 0) ok = false;
+                    }
+                    if (std::llabs(bias[j]) >= (1ll << 61)) ok = false;
+                }
+            }
+            if (ok) {
+                // fragment order: bfrag[ntile][digit][half][lane] = { b0(ks=2*half), b1(ks=2*half), b0(ks=2*half+1), b1(ks=2*half+1) }
+                // with b0 = digits of output bit 8*ntile + lane/4 at k = 32*ks + 4*(lane%4) .. +3 and b1 the same at k + 16
+                const int ntiles = nbits / 8;
+                std::vector<unsigned int> frag((size_t)ntiles * 6 * 2 * 32 * 4);
+                auto word = [&](int d, int j, int k) { unsigned int u; std::memcpy(&u, &dig[((size_t)d * nbits + j) * 128 + k], 4); return u; };
+                for (int nt = 0; nt < ntiles; nt++)
+                    for (int d = 0; d < 6; d++)
+                        for (int half = 0; half < 2; half++)
+                            for (int lane = 0; lane < 32; lane++) {
+                                const int j = nt * 8 + lane / 4, kq = 4 * (lane % 4);
+                                unsigned int* o = &frag[((((size_t)nt * 6 + d) * 2 + half) * 32 + lane) * 4];
+                                o[0] = word(d, j, 32 * (2 * half) + kq);     o[1] = word(d, j, 32 * (2 * half) + kq + 16);
+                                o[2] = word(d, j, 32 * (2 * half + 1) + kq); o[3] = word(d, j, 32 * (2 * half + 1) + kq + 16);
+                            }
+                EF_CUDA(h, cudaMalloc(&h->d_hs_bfrag[v], frag.size() * sizeof(unsigned int)));
+                EF_CUDA(h, cudaMalloc(&h->d_hs_bias[v], bias.size() * sizeof(long long)));
+                EF_CUDA(h, cudaMemcpy(h->d_hs_bfrag[v], frag.data(), frag.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+                EF_CUDA(h, cudaMemcpy(h->d_hs_bias[v], bias.data(), bias.size() * sizeof(long long), cudaMemcpyHostToDevice));
+                h->hs_shift[v] = S;
+            }
+        }
     }
     // Finite-domain libm tables of the CPU reference (constants, filled once per handle with the host's
     // libm -- the same libm the reference's CPU build links, which is what "bit-exact vs CPU" means):
@@ -272,7 +323,6 @@ int allocate(ef_handle* h)
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { total += bytes; return cudaMalloc(ptr, bytes ? bytes : 1); };
     EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
     EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
-    EF_CUDA(h, alloc((void**)&h->d_nms_offsets, sizeof(int) * 129 * 129));
     h->sift_rows = std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
     EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
     EF_CUDA(h, alloc((void**)&h->d_integral, (size_t)(p.max_width + 1) * (p.max_height + 1) * 4));
@@ -300,19 +350,16 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
     if (w > p.max_width || hh > p.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than max_width x max_height of the handle");
     if (nframes < 1 || nframes > p.max_batch) return fail(h, EF_ERR_CAPACITY, "nframes exceeds max_batch of the handle");
     if (w < 32 || hh < 32) return fail(h, EF_ERR_BAD_ARG, "image smaller than 32x32");
-    int rc = build_nms_offsets(h);
-    if (rc != EF_OK) return rc;
     Geometry& g = h->glast;
     compute_geometry(w, hh, p.scale_factor, p.nlevels, p.nfeatures, g);
     std::memset(&P, 0, sizeof(P));
     P.nlevels = p.nlevels; P.first_level = p.first_level; P.nframes = nframes;
-    P.fast_threshold = p.fast_threshold; P.nms_r2 = h->nms_r2; P.nms_R = h->nms_R; P.nms_noffsets = h->nms_noffsets;
-    std::memcpy(P.nms_stage_end, h->nms_stage_end, sizeof(P.nms_stage_end));
+    const NmsGeom ng = nms_geometry(p.nonmax_radius);
+    P.fast_threshold = p.fast_threshold; P.nms_r2 = ng.r2; P.nms_R = ng.R; P.nms_block = ng.block; P.nms_K = ng.K;
     P.nfeatures = p.nfeatures;
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
     P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
     P.counters = h->d_counters;
-    P.nms_offsets = h->d_nms_offsets;
     int tiles = 0, btiles = 0, bands = 0, kblocks = 0;
     for (int l = 0; l < p.nlevels; l++) {
         EfLevel& L = P.lv[l];
@@ -321,6 +368,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
         if (L.w < 1 || L.h < 1) return fail(h, EF_ERR_BAD_ARG, "pyramid level degenerates to zero size; reduce nlevels");
         L.img_pitch = q.img_pitch; L.blur_pitch = q.img_pitch; L.resp_pitch = q.resp_pitch;
         L.tiles_x = ef_div_up(L.w, EF_TILE); L.tiles_y = ef_div_up(L.h, EF_TILE);
+        L.blk_w = ng.block ? ef_div_up(L.w, ng.block) : 0; L.blk_h = ng.block ? ef_div_up(L.h, ng.block) : 0;
         L.blur_tiles_x = ef_div_up(L.w, 64);
         L.quota = g.quota[l];
         L.surv_cap = (int)std::max(1l, lrint(0.1 * (double)L.w * L.h)); // CORNER_DENSITY, cuda_efficient_features.cpp:35,252
@@ -329,7 +377,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
             L.rx = (float)(1.0 / ((double)L.w / g.w[l - 1]));
             L.ry = (float)(1.0 / ((double)L.h / g.h[l - 1]));
         }
-        L.img_off = q.img_off; L.blur_off = q.blur_off; L.resp_off = q.resp_off; L.mask_off = q.mask_off;
+        L.img_off = q.img_off; L.blur_off = q.blur_off; L.resp_off = q.resp_off; L.blk_off = q.blk_off; L.mask_off = q.mask_off;
         L.rowcnt_off = q.rowcnt_off; L.surv_off = q.surv_off; L.sel_off = q.sel_off;
         L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks;
         if (l >= p.first_level) {
@@ -379,7 +427,8 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
             EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
-            ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, h->d_hs_weights_t[v], P.desc_bytes * 8,
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+            ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, P.desc_bytes * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, h->keep_proj ? h->d_proj : nullptr, s);
             mark(h, EF_STAGE_PROJECT, s);
         }
@@ -424,7 +473,6 @@ int ef_create(const ef_params* params, ef_handle** out)
     if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return EF_ERR_CUDA; }
     rc = allocate(h);
     if (rc == EF_OK) rc = upload_tables(h);
-    if (rc == EF_OK) rc = build_nms_offsets(h);
     if (rc != EF_OK) { std::fprintf(stderr, "ef_create: %s\n", h->err.c_str()); free_all(h); delete h; return rc; }
     *out = h;
     return EF_OK;
@@ -456,7 +504,8 @@ int ef_set_param(ef_handle* h, int id, double value)
     std::string why;
     int rc = validate(q, why);
     if (rc != EF_OK) return fail(h, rc, why);
-    const bool replan = q.nfeatures > h->prm.nfeatures || q.nlevels != h->prm.nlevels || q.scale_factor != h->prm.scale_factor;
+    const bool replan = q.nfeatures > h->prm.nfeatures || q.nlevels != h->prm.nlevels || q.scale_factor != h->prm.scale_factor ||
+                        nms_geometry(q.nonmax_radius).block != nms_geometry(h->prm.nonmax_radius).block;
     if (q.max_keypoints < q.nfeatures) q.max_keypoints = q.nfeatures;
     h->prm = q;
     if (replan) {
@@ -472,7 +521,7 @@ int ef_set_param(ef_handle* h, int id, double value)
         if (rc == EF_OK && h->keep_proj) rc = ef_debug_keep_projection(h, 1);
         if (rc != EF_OK) return rc;
     }
-    return build_nms_offsets(h);
+    return EF_OK;
 }
 
 int ef_get_param(const ef_handle* h, int id, double* value)
@@ -539,7 +588,8 @@ static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int 
     } else {
         EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
         ef_launch_hashsift_features_flat(job, t, h->d_sift128, s);
-        ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, h->d_hs_weights_t[v], job.nbits, d_desc, 0, (int)desc_pitch,
+        const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+        ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, pt, job.nbits, d_desc, 0, (int)desc_pitch,
                                          h->keep_proj ? h->d_proj : nullptr, s);
     }
     EF_CUDA(h, cudaGetLastError());

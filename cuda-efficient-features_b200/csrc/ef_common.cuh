@@ -18,7 +18,10 @@
 #define EF_TILE 32                // square pixel tile of the score / NMS kernels
 #define EF_NEG_INF (__int_as_float(0xff800000))
 
-struct __align__(8) EfSurvivor { short x, y; float resp; };                 // compacted NMS survivor
+struct __align__(8) EfSurvivor { short x, y; float resp; };
+// NMS block-maximum map entry: largest response of a b x b pixel block (-inf: no corner) and where it is:
+// pos = tie << 31 | y << 16 | x (level coordinates; tie: the maximum is attained by more than one pixel)
+struct __align__(8) EfBlockMax { float val; unsigned pos; };                 // compacted NMS survivor
 struct __align__(16) EfSelected { short x, y; float resp; float angle; int pad; }; // per-level selected keypoint (level coords)
 
 // per-frame, per-level counters (zeroed at the start of every call)
@@ -30,6 +33,7 @@ struct EfLevel {
     int blur_pitch;     // bytes
     int resp_pitch;     // floats
     int tiles_x, tiles_y;
+    int blk_w, blk_h;   // dimensions of the NMS block-maximum map (ceil(w / nms_block), ceil(h / nms_block))
     int tile_start;     // first tile index of this level in the all-level tile table
     int blur_tile_start, blur_tiles_x; // 64x32 blur tiles
     int band_start;     // first 32-row band index of this level
@@ -39,12 +43,14 @@ struct EfLevel {
     float scale;        // scales_[s]
     float rx, ry;       // resize ratios src/dst for producing THIS level from the previous one
     // byte offsets inside one frame slot of the workspace
-    unsigned long long img_off, blur_off, resp_off, mask_off, rowcnt_off, surv_off, sel_off;
+    unsigned long long img_off, blur_off, resp_off, blk_off, mask_off, rowcnt_off, surv_off, sel_off;
 };
 
 struct EfPipe {
     int nlevels, first_level, nframes;
-    int fast_threshold, nms_r2, nms_R, nms_noffsets;
+    int fast_threshold;
+    int nms_r2, nms_R;          // ceil(r^2); largest |d| with d^2 < nms_r2
+    int nms_block, nms_K;       // block edge of the block-maximum map (0: r2 <= 1, nothing is suppressed); block reach of the disc
     int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks;
     int nfeatures;              // output capacity (columns)
     int desc_type, desc_bytes;
@@ -56,8 +62,6 @@ struct EfPipe {
     // workspace
     uint8_t* ws; unsigned long long ws_stride;           // per-frame slot
     EfLevelCounters* counters; /* [frame][EF_MAX_LEVELS] */
-    const int* nms_offsets;                               // disc offsets (dy*SW+dx in the NMS smem tile) sorted by Chebyshev ring
-    int nms_stage_end[4];                                 // offsets [0,e0) ring<=1, [e0,e1) ring<=3, [e1,e2) ring<=7, rest
     EfLevel lv[EF_MAX_LEVELS];
 };
 
@@ -129,10 +133,12 @@ void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s);
 struct EfHashSiftTables { const float* exp_table; /*30x30*/ const float* atan2_table; /*511x511*/ const float* weights; /*nbits x 129*/ };
 void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
 void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
-// projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8); row_map == nullptr: desc row i = i.
-void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const float* weights, int nbits,
+// projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8).  bfrag != nullptr: exact integer-tensor-core
+// path (fixed-point digits of the weights in mma fragment order, int64 bias, scale 2^-shift); else fp64 fallback on weights_t.
+struct EfProjTables { const uint4* bfrag; const long long* bias; int shift; const float* weights_t; /*129 x nbits*/ };
+void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const EfProjTables& t, int nbits,
                                 uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s);
-void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
+void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
                                       uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s);
 // 5xN keypoint rows -> n x float4 (x, y, 31, angle): convertKeypointsKernel, cuda_efficient_features.cu:250-263
 void ef_launch_convert_rows(const float* kpts5, size_t kpts_pitch, int n, float4* out, cudaStream_t s);

@@ -543,94 +543,6 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 }
 
 // =================================================================================================
-// HashSIFT projection + sign + pack (hash_sift.cpp:353-378), exact: out = float32(sum_k a_k * w_k) with
-// the sum carried in double in ascending k (every product u8 x fp32 is exact in double).
-// weights_t: 129 x nbits (transposed at create).  16 keypoints per CTA, one output bit column per thread.
-// =================================================================================================
-#define EF_PROJ_KP 16
-template <int NCOL>
-__global__ void __launch_bounds__(256) ef_hashsift_project_kernel(const uint8_t* __restrict__ sift128, int n_cap, const int* __restrict__ d_n,
-                                                                  size_t frame_rows, const float* __restrict__ weights_t,
-                                                                  uint8_t* __restrict__ desc, size_t desc_stride, int desc_pitch,
-                                                                  float* __restrict__ proj_out)
-{
-    constexpr int nbits = 256 * NCOL;
-    __shared__ __align__(16) double s_a[129][EF_PROJ_KP]; // [k][keypoint]: one 16-byte broadcast load feeds 2 keypoints
-    const int frame = blockIdx.y;
-    const int n = d_n ? min(d_n[frame], n_cap) : n_cap;
-    const int k0 = blockIdx.x * EF_PROJ_KP;
-    if (k0 >= n) return;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint8_t* src = sift128 + (size_t)frame * frame_rows * 128;
-    for (int i = tid; i < EF_PROJ_KP * 129; i += 256) {
-        const int kk = i / 129, k = i - kk * 129;
-        double v = 0.0;
-        if (k0 + kk < n) v = (k == 0) ? 1.0 : (double)src[(size_t)(k0 + kk) * 128 + (k - 1)];
-        s_a[k][kk] = v;
-    }
-    __syncthreads();
-    double acc[NCOL][EF_PROJ_KP];
-#pragma unroll
-    for (int c = 0; c < NCOL; c++)
-#pragma unroll
-        for (int kk = 0; kk < EF_PROJ_KP; kk++) acc[c][kk] = 0.0;
-    for (int k = 0; k < 129; k++) {
-        double wv[NCOL];
-#pragma unroll
-        for (int c = 0; c < NCOL; c++) wv[c] = (double)__ldg(weights_t + (size_t)k * nbits + tid + 256 * c);
-#pragma unroll
-        for (int kp = 0; kp < EF_PROJ_KP; kp += 2) {
-            const double2 a = *reinterpret_cast<const double2*>(&s_a[k][kp]);
-#pragma unroll
-            for (int c = 0; c < NCOL; c++) {
-                acc[c][kp] = fma(a.x, wv[c], acc[c][kp]);
-                acc[c][kp + 1] = fma(a.y, wv[c], acc[c][kp + 1]);
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < NCOL; c++) {
-        const int j = tid + 256 * c;
-#pragma unroll
-        for (int kk = 0; kk < EF_PROJ_KP; kk++) {
-            const float tv = (float)acc[c][kk];
-            const bool valid = k0 + kk < n;
-            const unsigned bal = __brev(__ballot_sync(0xffffffffu, tv > 0));
-            if (valid) {
-                if (proj_out) proj_out[((size_t)frame * frame_rows + k0 + kk) * nbits + j] = tv;
-                if (lane < 4)
-                    desc[(size_t)frame * desc_stride + (size_t)(k0 + kk) * desc_pitch + ((j & ~31) >> 3) + lane] = (uint8_t)(bal >> (24 - 8 * lane));
-            }
-        }
-    }
-}
-
-static void ef_project_launch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
-                              uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
-{
-    const dim3 grid(ef_div_up(n_cap, EF_PROJ_KP), nframes);
-    if (nbits == 256)
-        ef_hashsift_project_kernel<1><<<grid, 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, desc, desc_stride, desc_pitch, proj_out);
-    else
-        ef_hashsift_project_kernel<2><<<grid, 256, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, weights, desc, desc_stride, desc_pitch, proj_out);
-    EF_COUNT_LAUNCH(1);
-}
-
-void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const float* weights, int nbits,
-                                uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s)
-{
-    if (n_cap <= 0) return;
-    ef_project_launch(sift128, n_cap, d_n, 1, weights, nbits, desc, 0, desc_pitch, proj_out, s);
-}
-
-void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const float* weights, int nbits,
-                                      uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
-{
-    if (n_cap <= 0 || nframes <= 0) return;
-    ef_project_launch(sift128, n_cap, d_counts, nframes, weights, nbits, desc, desc_stride, desc_pitch, proj_out, s);
-}
-
-// =================================================================================================
 // convertKeypointsKernel (cuda_efficient_features.cu:250-263): 5 x N rows -> (x, y, PATCH_SIZE, angle)
 // =================================================================================================
 __global__ void ef_convert_rows_kernel(const uint8_t* __restrict__ kpts5, size_t pitch, int n, float4* __restrict__ out)

@@ -194,6 +194,53 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
     }
     __syncthreads();
 
+    // ---- block maxima for the NMS stage: largest response per b x b block, its position, tie flag
+    if (p.nms_block > 0) {
+        EfBlockMax* bmap = reinterpret_cast<EfBlockMax*>(ef_ws(p, frame, L.blk_off));
+        if (p.nms_block == 8) {
+            // 16 blocks per tile, 16 threads per block (half-warp), one float4 per thread
+            const int blk = tid >> 4, sub = tid & 15;
+            const int by = blk >> 2, bx = blk & 3;
+            const int row = by * 8 + (sub >> 1), col = bx * 8 + (sub & 1) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(&s_resp[row][col]);
+            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            float g = m;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+            const bool has = (m == g);
+            const unsigned bal = (__ballot_sync(0xffffffffu, has) >> (lane & 16)) & 0xffffu;
+            const int gbx = (x0 >> 3) + bx, gby = (y0 >> 3) + by;
+            if (gbx < L.blk_w && gby < L.blk_h && has && (__ffs(bal) - 1) == sub) {
+                EfBlockMax e;
+                e.val = g; e.pos = 0;
+                if (g > EF_NEG_INF) {
+                    const int cnt = (v.x == g) + (v.y == g) + (v.z == g) + (v.w == g);
+                    const int j = (v.x == g) ? 0 : (v.y == g) ? 1 : (v.z == g) ? 2 : 3;
+                    const unsigned tie = (__popc(bal) > 1 || cnt > 1) ? 0x80000000u : 0u;
+                    e.pos = tie | ((unsigned)(y0 + row) << 16) | (unsigned)(x0 + col + j);
+                }
+                bmap[(size_t)gby * L.blk_w + gbx] = e;
+            }
+        } else {
+            const int b = p.nms_block, nb = EF_TILE / b;
+            for (int blk = tid; blk < nb * nb; blk += 256) {
+                const int by = blk / nb, bx = blk - by * nb;
+                const int gbx = x0 / b + bx, gby = y0 / b + by;
+                if (gbx >= L.blk_w || gby >= L.blk_h) continue;
+                float g = EF_NEG_INF; int cnt = 0; unsigned pos = 0;
+                for (int yy = 0; yy < b; yy++)
+                    for (int xx = 0; xx < b; xx++) {
+                        const float v = s_resp[by * b + yy][bx * b + xx];
+                        if (v > g) { g = v; cnt = 1; pos = ((unsigned)(y0 + by * b + yy) << 16) | (unsigned)(x0 + bx * b + xx); }
+                        else if (v == g) cnt++;
+                    }
+                EfBlockMax e;
+                e.val = g; e.pos = (g > EF_NEG_INF) ? (pos | (cnt > 1 ? 0x80000000u : 0u)) : 0u;
+                bmap[(size_t)gby * L.blk_w + gbx] = e;
+            }
+        }
+    }
+
     // ---- dense response map, one float4 per thread (resp_pitch is a multiple of 32 floats)
     {
         const int row = tid >> 3, c4 = (tid & 7) * 4;
@@ -214,26 +261,24 @@ void ef_launch_score(const EfPipe& p, cudaStream_t s)
 }
 
 // =================================================================================================
-// radius NMS on the dense map: tile + halo in shared memory.
-//   i dies iff exists j != i with resp_i <= resp_j and dx^2+dy^2 < ceil(r^2)   (cuda_efficient_features.cu:90)
-// Two phases (ncu of the first version showed 69 % of the time at a barrier behind 5-thread-wide tails):
-//   1. one thread per pixel tests the innermost ring (Chebyshev distance 1) and the still-alive
-//      candidates are ballot-compacted into a list (kills ~2/3 of the corners on noise);
-//   2. one WARP per listed candidate scans the rest of the disc, 32 offsets per step in ring order,
-//      and stops at the first step that finds a stronger-or-equal neighbour (warp vote).
+// radius NMS.   i dies iff exists j != i with resp_i <= resp_j and dx^2+dy^2 < ceil(r^2)   (cuda_efficient_features.cu:90)
+//
+// The score stage leaves, next to the dense response map, the maximum of every b x b pixel block
+// (b = 8 for the default radius 15) with its position.  b is chosen so that a whole block lies inside
+// the disc of each of its pixels (2(b-1)^2 < r^2), hence
+//   * only the unique maximum of a block can survive (everything else in the block is killed by it);
+//   * a candidate c is killed by block B iff some pixel of B inside c's disc has a response >= resp_c:
+//     if max(B) < resp_c nothing in B can; if max(B) >= resp_c and argmax(B) is inside the disc it does;
+//     only when max(B) >= resp_c sits OUTSIDE the disc are the pixels of B compared one by one (dense map).
+// One warp per candidate, one lane per neighbouring block ((2K+1)^2 = 25 for r = 15): the 29x29-pixel disc
+// scan of the reference becomes 25 eight-byte loads.  Pure comparisons: results are exact.
 // Output: one 32-bit survivor word per (tile,row) in tile-major order + per-row survivor counts.
 // =================================================================================================
+#define EF_NMS_MAX_SIDE 20 // blocks per side of the staged neighbourhood: 32/b + 2K <= 20 for every radius in [2, 64]
 __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfPipe p)
 {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ unsigned s_mask[EF_TILE];
-    __shared__ int s_cnt;
-
-    const int R = p.nms_R;
-    const int SW = EF_TILE + 2 * R;
-    float* s_r = reinterpret_cast<float*>(s_dyn);
-    int* s_off = reinterpret_cast<int*>(s_r + SW * SW);
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_off + p.nms_noffsets);
+    __shared__ EfBlockMax s_blk[EF_NMS_MAX_SIDE * EF_NMS_MAX_SIDE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
@@ -243,76 +288,74 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     const int x0 = (t % L.tiles_x) * EF_TILE, y0 = (t / L.tiles_x) * EF_TILE;
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
 
+    const int b = p.nms_block;
     if (tid < EF_TILE) s_mask[tid] = 0;
-    if (tid == 0) s_cnt = 0;
-    for (int i = tid; i < p.nms_noffsets; i += 256) s_off[i] = p.nms_offsets[i];
-    // tile + halo: warp <-> row, lane <-> column pair (8-byte loads when the halo is even: x0-R is then even)
-    if ((R & 1) == 0) {
-        const int npair = SW >> 1;
-        for (int ly = warp; ly < SW; ly += 8) {
-            const int gy = y0 - R + ly;
-            const bool rowin = gy >= 0 && gy < L.h;
-            const float* row = resp + (size_t)gy * L.resp_pitch;
-            for (int lp = lane; lp < npair; lp += 32) {
-                const int gx = x0 - R + 2 * lp;
-                float2 v = make_float2(EF_NEG_INF, EF_NEG_INF);
-                if (rowin && gx >= 0 && gx + 1 < L.resp_pitch) {
-                    v = *reinterpret_cast<const float2*>(row + gx);
-                    if (gx + 1 >= L.w) v.y = EF_NEG_INF;
-                    if (gx >= L.w) v.x = EF_NEG_INF;
-                }
-                *reinterpret_cast<float2*>(&s_r[ly * SW + 2 * lp]) = v;
-            }
+    if (b == 0) {
+        // r^2 <= 1: the disc holds only the pixel itself, every corner survives
+        __syncthreads();
+        for (int py = warp; py < EF_TILE; py += 8) {
+            const int gy = y0 + py, gx = x0 + lane;
+            const bool c = gy < L.h && gx < L.w && resp[(size_t)gy * L.resp_pitch + gx] > EF_NEG_INF;
+            const unsigned bal = __ballot_sync(0xffffffffu, c);
+            if (lane == 0) s_mask[py] = bal;
         }
     } else {
-        for (int ly = warp; ly < SW; ly += 8) {
-            const int gy = y0 - R + ly;
-            const bool rowin = gy >= 0 && gy < L.h;
-            for (int lx = lane; lx < SW; lx += 32) {
-                const int gx = x0 - R + lx;
-                float v = EF_NEG_INF;
-                if (rowin && gx >= 0 && gx < L.w) v = resp[(size_t)gy * L.resp_pitch + gx];
-                s_r[ly * SW + lx] = v;
+        // stage the block maxima of the tile and of the K blocks around it: one global round trip per CTA
+        const EfBlockMax* __restrict__ bmap = reinterpret_cast<const EfBlockMax*>(ef_ws(p, frame, L.blk_off));
+        const int nb = EF_TILE / b, K = p.nms_K, side = nb + 2 * K, r2 = p.nms_r2;
+        const int sbx0 = x0 / b - K, sby0 = y0 / b - K; // block coordinates of s_blk[0]
+        for (int i = tid; i < side * side; i += 256) {
+            const int gby = sby0 + i / side, gbx = sbx0 + i % side;
+            EfBlockMax e; e.val = EF_NEG_INF; e.pos = 0;
+            if (gbx >= 0 && gby >= 0 && gbx < L.blk_w && gby < L.blk_h) e = bmap[(size_t)gby * L.blk_w + gbx];
+            s_blk[i] = e;
+        }
+        __syncthreads();
+        const int wside = 2 * K + 1, nnb = wside * wside;
+        for (int c = warp; c < nb * nb; c += 8) {
+            const int ly = c / nb + K, lx = c % nb + K;                       // candidate block in s_blk coordinates
+            const EfBlockMax own = s_blk[ly * side + lx];
+            if (!(own.val > EF_NEG_INF) || (own.pos & 0x80000000u)) continue; // no corner, or a tie inside the block: both die
+            const float r = own.val;
+            const int cx = own.pos & 0xffff, cy = (own.pos >> 16) & 0x7fff;
+            bool dead = false;
+            for (int n0 = 0; n0 < nnb && !dead; n0 += 32) {
+                const int n = n0 + lane;
+                bool kill = false, scan = false;
+                int nbx = 0, nby = 0;
+                if (n < nnb && n != (nnb >> 1)) {                             // the centre of the window is the block itself
+                    const int wy = n / wside, wx = n - wy * wside;
+                    const EfBlockMax e = s_blk[(ly - K + wy) * side + lx - K + wx];
+                    if (e.val >= r) {
+                        const int ex = (int)(e.pos & 0xffff) - cx, ey = (int)((e.pos >> 16) & 0x7fff) - cy;
+                        if (ex * ex + ey * ey < r2) kill = true;
+                        else {
+                            // nearest pixel of the block to the candidate: outside the disc -> the block cannot kill
+                            nbx = sbx0 + lx - K + wx; nby = sby0 + ly - K + wy;
+                            const int bx0 = nbx * b, by0 = nby * b;
+                            const int qx = min(max(cx, bx0), bx0 + b - 1) - cx, qy = min(max(cy, by0), by0 + b - 1) - cy;
+                            scan = qx * qx + qy * qy < r2;
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, kill)) { dead = true; break; }
+                // rare: max(B) >= r lies outside the disc -> compare the pixels of B inside the disc one by one
+                unsigned todo = __ballot_sync(0xffffffffu, scan);
+                while (todo && !dead) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int px0 = __shfl_sync(0xffffffffu, nbx, src) * b, py0 = __shfl_sync(0xffffffffu, nby, src) * b;
+                    bool k2 = false;
+                    for (int q = lane; q < b * b; q += 32) {
+                        const int gx = px0 + q % b, gy = py0 + q / b;
+                        const int ddx = gx - cx, ddy = gy - cy;
+                        if (gx < L.w && gy < L.h && ddx * ddx + ddy * ddy < r2 && resp[(size_t)gy * L.resp_pitch + gx] >= r) k2 = true;
+                    }
+                    if (__any_sync(0xffffffffu, k2)) dead = true;
+                }
             }
+            if (!dead && lane == 0) atomicOr(&s_mask[cy & 31], 1u << (cx & 31));
         }
-    }
-    __syncthreads();
-
-    // phase 1: innermost ring per pixel, compaction of the still-alive corners
-    const int k1 = p.nms_stage_end[0];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int py = warp + 8 * i;
-        const int c = (py + R) * SW + lane + R;
-        const float ri = s_r[c];
-        bool alive = ri > EF_NEG_INF;
-        if (alive) {
-            for (int k = 0; k < k1; k++)
-                if (ri <= s_r[c + s_off[k]]) { alive = false; break; }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        const int cnt = __popc(bal);
-        int base = 0;
-        if (lane == 0 && cnt) base = atomicAdd(&s_cnt, cnt);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (alive) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((py << 5) | lane);
-    }
-    __syncthreads();
-
-    // phase 2: warp per candidate, 32 offsets per step, early exit on a warp vote
-    const int n = s_cnt;
-    const int noff = p.nms_noffsets;
-    for (int i = warp; i < n; i += 8) {
-        const int pos = s_list[i];
-        const int c = ((pos >> 5) + R) * SW + (pos & 31) + R;
-        const float ri = s_r[c];
-        bool alive = true;
-        for (int kb = k1; kb < noff; kb += 32) {
-            const int k = kb + lane;
-            const bool kill = k < noff && ri <= s_r[c + s_off[k]];
-            if (__any_sync(0xffffffffu, kill)) { alive = false; break; }
-        }
-        if (alive && lane == 0) atomicOr(&s_mask[pos >> 5], 1u << (pos & 31));
     }
     __syncthreads();
 
@@ -328,22 +371,10 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     }
 }
 
-static size_t ef_nms_smem_bytes(const EfPipe& p)
-{
-    const int SW = EF_TILE + 2 * p.nms_R;
-    return (size_t)SW * SW * sizeof(float) + (size_t)p.nms_noffsets * sizeof(int) + EF_TILE * EF_TILE * sizeof(unsigned short);
-}
-
 void ef_launch_nms(const EfPipe& p, cudaStream_t s)
 {
     if (p.total_tiles <= 0) return;
-    const size_t smem = ef_nms_smem_bytes(p);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(ef_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
-    ef_nms_kernel<<<dim3(p.total_tiles, p.nframes), 256, smem, s>>>(p);
+    ef_nms_kernel<<<dim3(p.total_tiles, p.nframes), 256, 0, s>>>(p);
     EF_COUNT_LAUNCH(1);
 }
 

@@ -121,11 +121,13 @@ def test_hashsift_compute(torch_cuda, oracle, nbits):
     sift, proj = hs._ef.debugHashSift(len(k))
     feat = oracle.hashsift_features(img, k, 1.0)
     o, oproj = oracle.hashsift(img, k, 1.0, nbits, want_proj=True)
-    # 128-vector (u8-valued) identical; projection = float32(exact dot): 0 ULP (tolerance of north_star: 1 ULP); bits identical
+    # 128-vector (u8-valued) identical; bits identical.  Projection: the GPU value is float32(EXACT dot product) (integer
+    # tensor cores, one rounding), the oracle's is float32(double accumulation in ascending k): tolerance 1 ULP (the
+    # north_star tolerance), and they may differ only through a double-rounding event (< 1e-6 of the outputs)
     assert np.array_equal(sift, feat[:, 1:].astype(np.uint8)), f"{(sift != feat[:, 1:]).any(axis=1).sum()} of {len(k)} SIFT vectors differ"
     ulp = np.abs(proj.view(np.int32).astype(np.int64) - oproj.view(np.int32).astype(np.int64))
     assert ulp.max() <= 1 and (np.sign(proj) == np.sign(oproj)).all(), f"projection differs by up to {ulp.max()} ULP"
-    assert np.array_equal(proj.view(np.uint32), oproj.view(np.uint32))
+    assert (ulp != 0).mean() < 1e-6, f"{(ulp != 0).sum()} projection values differ from the oracle"
     assert np.array_equal(g, o)
 
 
