@@ -100,7 +100,7 @@ struct ef_handle {
     long long* d_hs_bias[2] = { nullptr, nullptr };  // column 0 of the projection as fixed-point integers
     int hs_shift[2] = { 0, 0 };                      // fixed-point scale 2^-shift; bfrag == nullptr: table does not fit 6 digits
     float* d_exp_table = nullptr;
-    float* d_atan2_table = nullptr;
+    float2* d_grad_table = nullptr;
 
     uint8_t* d_sift128 = nullptr;   // max(max_batch*nfeatures, max_keypoints) x 128
     float* d_proj = nullptr;        // optional debug: rows x 512
@@ -150,7 +150,7 @@ void free_all(ef_handle* h)
 {
     cudaFree(h->d_ws); cudaFree(h->d_counters);
     for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); cudaFree(h->d_hs_bfrag[i]); cudaFree(h->d_hs_bias[i]); }
-    cudaFree(h->d_exp_table); cudaFree(h->d_atan2_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
+    cudaFree(h->d_exp_table); cudaFree(h->d_grad_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
     cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
     cudaFree(h->d_in); cudaFree(h->d_out_kpts); cudaFree(h->d_out_desc); cudaFree(h->d_out_counts);
     if (h->h_counts_pinned) cudaFreeHost(h->h_counts_pinned);
@@ -292,9 +292,12 @@ int upload_tables(ef_handle* h)
     // Finite-domain libm tables of the CPU reference (constants, filled once per handle with the host's
     // libm -- the same libm the reference's CPU build links, which is what "bit-exact vs CPU" means):
     //   expf(distScale * ((x-15)^2 + (y-15)^2)) for the 30x30 gradient positions (hash_sift.cpp:220-224,247)
-    //   atan2f(dy, dx) for dy, dx in [-255, 255]                                  (hash_sift.cpp:250-254)
+    //   for dy, dx in [-255, 255] (hash_sift.cpp:247-260): sqrtf(dx^2 + dy^2), and from ori = atan2f(dy, dx):
+    //   ob = (8 / 2pi) * ori, bin = floor(ob) wrapped into [0,8), fraction = ob - floor(ob).  The 3-bit bin is packed
+    //   into the sign bit of the sqrt (bit 2) and bits 31:30 of the fraction (< 1, so both are free).
     {
-        std::vector<float> et(900), at((size_t)511 * 511);
+        std::vector<float> et(900);
+        std::vector<float2> gt((size_t)511 * 511);
         const float kpScale = 1.f / 6;
         const float kpRadius = kpScale * 32.f * 0.5f;
         const float kernelSigma = 0.5f * 4 * 3.f * kpRadius;
@@ -305,12 +308,31 @@ int upload_tables(ef_handle* h)
                 const float fx = (float)x - cx, fy = (float)y - cy;
                 et[y * 30 + x] = expf(distScale * (fx * fx + fy * fy));
             }
-        for (int dy = -255; dy <= 255; dy++)
-            for (int dx = -255; dx <= 255; dx++) at[(size_t)(dy + 255) * 511 + (dx + 255)] = atan2f((float)dy, (float)dx);
+        const float PI_2_0F = 6.28318548f;
+        const float scaleO = 8 / PI_2_0F;
+        for (int dyi = -255; dyi <= 255; dyi++)
+            for (int dxi = -255; dxi <= 255; dxi++) {
+                const float dx = (float)dxi, dy = (float)dyi;
+                const float mag = sqrtf(dx * dx + dy * dy);
+                const float ori = atan2f(dy, dx);
+                const float ob = scaleO * ori;
+                int oi = (int)floorf(ob);
+                const float of = ob - (float)oi;
+                if (oi < 0) oi += 8;
+                if (oi >= 8) oi -= 8;
+                unsigned mb, fb;
+                std::memcpy(&mb, &mag, 4); std::memcpy(&fb, &of, 4);
+                if ((fb >> 30) != 0 || oi < 0 || oi > 7) return fail(h, EF_ERR_UNSUPPORTED, "orientation fraction outside [0,1): host libm atan2f out of range");
+                mb |= (unsigned)(oi >> 2) << 31;
+                fb |= (unsigned)(oi & 3) << 30;
+                float2 e;
+                std::memcpy(&e.x, &mb, 4); std::memcpy(&e.y, &fb, 4);
+                gt[(size_t)(dyi + 255) * 511 + (dxi + 255)] = e;
+            }
         EF_CUDA(h, cudaMalloc(&h->d_exp_table, et.size() * sizeof(float)));
-        EF_CUDA(h, cudaMalloc(&h->d_atan2_table, at.size() * sizeof(float)));
+        EF_CUDA(h, cudaMalloc(&h->d_grad_table, gt.size() * sizeof(float2)));
         EF_CUDA(h, cudaMemcpy(h->d_exp_table, et.data(), et.size() * sizeof(float), cudaMemcpyHostToDevice));
-        EF_CUDA(h, cudaMemcpy(h->d_atan2_table, at.data(), at.size() * sizeof(float), cudaMemcpyHostToDevice));
+        EF_CUDA(h, cudaMemcpy(h->d_grad_table, gt.data(), gt.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
     return EF_OK;
 }
@@ -360,7 +382,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
     P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
     P.counters = h->d_counters;
-    int tiles = 0, btiles = 0, bands = 0, kblocks = 0;
+    int tiles = 0, btiles = 0, bands = 0, kblocks = 0, sblocks = 0, strips = 0;
     for (int l = 0; l < p.nlevels; l++) {
         EfLevel& L = P.lv[l];
         const LevelPlan& q = h->plan[l];
@@ -379,15 +401,18 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
         }
         L.img_off = q.img_off; L.blur_off = q.blur_off; L.resp_off = q.resp_off; L.blk_off = q.blk_off; L.mask_off = q.mask_off;
         L.rowcnt_off = q.rowcnt_off; L.surv_off = q.surv_off; L.sel_off = q.sel_off;
-        L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks;
+        L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks; L.sift_block_start = sblocks;
+        L.strips_x = ef_div_up(L.tiles_x, 4); L.strip_start = strips;
         if (l >= p.first_level) {
             tiles += L.tiles_x * L.tiles_y;
+            strips += L.strips_x * L.tiles_y;
             bands += L.tiles_y;
             kblocks += ef_div_up(std::min(L.quota, p.nfeatures), 8);
+            sblocks += ef_div_up(std::min(L.quota, p.nfeatures), 4);
             btiles += L.blur_tiles_x * ef_div_up(L.h, 32);
         }
     }
-    P.total_tiles = tiles; P.total_blur_tiles = btiles; P.total_bands = bands; P.total_kpt_blocks = kblocks;
+    P.total_tiles = tiles; P.total_blur_tiles = btiles; P.total_bands = bands; P.total_kpt_blocks = kblocks; P.total_sift_blocks = sblocks; P.total_strips = strips;
     h->last_w = w; h->last_h = hh; h->last_nframes = nframes;
     return EF_OK;
 }
@@ -424,7 +449,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
             ef_launch_bad_pipe(P, t, s);
             mark(h, EF_STAGE_DESCRIBE, s);
         } else {
-            EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
+            EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
             const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
@@ -586,7 +611,7 @@ static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int 
         EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
         ef_launch_bad_flat(job, h->d_integral, t, s);
     } else {
-        EfHashSiftTables t{ h->d_exp_table, h->d_atan2_table, h->d_hs_weights_t[v] };
+        EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
         ef_launch_hashsift_features_flat(job, t, h->d_sift128, s);
         const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
         ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, pt, job.nbits, d_desc, 0, (int)desc_pitch,

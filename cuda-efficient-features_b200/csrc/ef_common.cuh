@@ -35,11 +35,13 @@ struct EfLevel {
     int tiles_x, tiles_y;
     int blk_w, blk_h;   // dimensions of the NMS block-maximum map (ceil(w / nms_block), ceil(h / nms_block))
     int tile_start;     // first tile index of this level in the all-level tile table
+    int strips_x, strip_start; // NMS strips of 4 tiles per tile row; first strip index of this level
     int blur_tile_start, blur_tiles_x; // 64x32 blur tiles
     int band_start;     // first 32-row band index of this level
     int quota;          // nfeaturesPerLevel_[s]
     int surv_cap;       // capacity of the survivor list
-    int kpt_block_start;// first descriptor-CTA index of this level (quota / kpts-per-CTA, rounded up)
+    int kpt_block_start;// first descriptor-CTA index of this level (quota / 8 keypoints per CTA, rounded up)
+    int sift_block_start;// same for the HashSIFT feature kernel (4 keypoints per CTA)
     float scale;        // scales_[s]
     float rx, ry;       // resize ratios src/dst for producing THIS level from the previous one
     // byte offsets inside one frame slot of the workspace
@@ -51,7 +53,7 @@ struct EfPipe {
     int fast_threshold;
     int nms_r2, nms_R;          // ceil(r^2); largest |d| with d^2 < nms_r2
     int nms_block, nms_K;       // block edge of the block-maximum map (0: r2 <= 1, nothing is suppressed); block reach of the disc
-    int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks;
+    int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks, total_sift_blocks, total_strips;
     int nfeatures;              // output capacity (columns)
     int desc_type, desc_bytes;
     // caller buffers (frame f at base + f*stride)
@@ -130,7 +132,9 @@ void ef_launch_integral(const uint8_t* img, int w, int h, int pitch, unsigned* i
 void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const EfBadTables& t, cudaStream_t s);
 void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s);
 
-struct EfHashSiftTables { const float* exp_table; /*30x30*/ const float* atan2_table; /*511x511*/ const float* weights; /*nbits x 129*/ };
+// exp_table: expf weight of the 30x30 gradient positions; grad_table[(dy+255)*511 + dx+255] = { sqrtf(dx^2+dy^2) with the sign bit = bit 2 of
+// the orientation bin, orientation-bin fraction with bits 31:30 = bits 1:0 of the bin } (see ef_hashsift.cu, ef_api.cu)
+struct EfHashSiftTables { const float* exp_table; const float2* grad_table; };
 void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
 void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
 // projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8).  bfrag != nullptr: exact integer-tensor-core

@@ -8,7 +8,6 @@
 // Compiled with -fmad=false: the CPU reference is a generic x86-64 build without FMA, so every
 // a*b+c below must stay two roundings.
 #include "ef_common.cuh"
-#include "ef_libm_f32.cuh"
 
 #include <cfloat>
 
@@ -294,251 +293,6 @@ void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
         configured = true;
     }
     ef_bad_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t);
-    EF_COUNT_LAUNCH(1);
-}
-
-// =================================================================================================
-// HashSIFT features: rectified 32x32 patch -> deterministic 4x4x8 gradient histogram -> 128 u8
-//
-// One HALF-WARP per keypoint (2 keypoints per warp, 8 per 128-thread CTA).  In the histogram phase lane c of
-// the half-warp owns histogram cell c (4x4 cells) and walks the <= 16x16 pixels that feed it in raster
-// order, adding the two orientation shares into ITS OWN 10 accumulators in shared memory (dynamic bin
-// index, no atomics, no cross-lane sharing): every accumulator receives exactly the CPU's sequence of
-// additions (hash_sift.cpp:233-290), so the 128-vector is bit-identical, unlike the reference GPU kernel's
-// shared-memory float atomics (cuda_hash_sift.cu:282-289).
-// =================================================================================================
-#define EF_SIFT_KP_PER_CTA 8
-#define EF_SIFT_PIX 912   // 30x30 gradient pixels stored at y*30 + x + 2*(y>>3): the skew spreads the 16 cells over 16 banks
-struct EfSiftSmem {       // per keypoint
-    float mag[EF_SIFT_PIX];
-    float of[EF_SIFT_PIX];
-    float hist[16 * 11];  // [cell][bin 0..9], pitch 11
-    float desc[128];
-    uint8_t patch[32 * 32];
-    uint8_t oi[EF_SIFT_PIX];
-};
-struct EfSiftBins { float bf[32]; int bi[32]; }; // per CTA: bin of patch row/col r = y+1 (index y)
-
-// hist row/col bin of patch row r = y+1 (hash_sift.cpp:179-180,186-191): scale * (r - 16) + 1.5, scale = 1/8
-__device__ __forceinline__ void ef_sift_bin(int r, int& bi, float& bf)
-{
-    const float kpScale = 1.f / 6;
-    const float cell = 3.f * (kpScale * 32.f * 0.5f);
-    const float scale = 1.f / cell;
-    const float b = scale * ((float)r - 16.f) + 1.5f;
-    bi = (int)floorf(b);
-    bf = b - (float)bi;
-}
-
-// normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
-__device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
-{
-    float sum = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 128; i++) { const float v = d[i]; sum += v * v; }
-    const float nrm = fmaxf(sqrtf(sum), FLT_EPSILON);
-    const float scale = 1.f / nrm;
-    __syncwarp();
-    for (int i = hl; i < 128; i += 16) d[i] *= scale;
-    __syncwarp();
-}
-
-// All 32 lanes call this; lanes 0-15 work on one keypoint, lanes 16-31 on another (sm, kx.. differ per half).
-__device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
-                                                float kx, float ky, float size, float angle, float croppingScale,
-                                                const EfHashSiftTables& t, EfSiftSmem& sm, const EfSiftBins& bins,
-                                                uint8_t* out128, bool store, int hl)
-{
-    // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
-    {
-        const float PI_1_0F = 3.14159274f;
-        const float s = croppingScale * size / (0.5f * (float)(32 + 32));
-        const float theta = PI_1_0F * angle / 180;
-        // cosf/sinf: the host libm's algorithm, bit for bit (ef_libm_f32.cuh)
-        const float cost = s * (angle >= 0 ? ef_libm::cosf_glibc(theta) : 1.f);
-        const float sint = s * (angle >= 0 ? ef_libm::sinf_glibc(theta) : 0.f);
-        const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
-        const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
-        for (int y = 0; y < 32; y++) {
-#pragma unroll
-            for (int xx = 0; xx < 2; xx++) {
-                const int x = hl + 16 * xx;
-                const float u = M00 * (float)x + M01 * (float)y + M02;
-                const float v = M10 * (float)x + M11 * (float)y + M12;
-                uint8_t dstVal = 0;
-                const int ui = (int)floorf(u);
-                const int vi = (int)floorf(v);
-                if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
-                    const uint8_t* q = img + (size_t)vi * pitch + ui;
-                    const float du = u - (float)ui;
-                    const float dv = v - (float)vi;
-                    const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
-                    const float tmp1 = (1 - du) * (float)q[pitch] + du * (float)q[pitch + 1];
-                    const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
-                    dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
-                }
-                sm.patch[y * 32 + x] = dstVal;
-            }
-        }
-    }
-    for (int j = hl; j < 16 * 11; j += 16) sm.hist[j] = 0.f;
-    __syncwarp();
-    // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260). expf over the 30x30 positions and
-    //      atan2f over dy,dx in [-255,255] are finite-domain tables (see ef_api.cu)
-    {
-        const float PI_2_0F = 6.28318548f;
-        const float scaleO = 8 / PI_2_0F;
-        for (int i = hl; i < 900; i += 16) {
-            const int y = i / 30, x = i - y * 30;
-            const int dxi = (int)sm.patch[(y + 1) * 32 + x + 2] - (int)sm.patch[(y + 1) * 32 + x];
-            const int dyi = (int)sm.patch[y * 32 + x + 1] - (int)sm.patch[(y + 2) * 32 + x + 1];
-            const float dx = (float)dxi, dy = (float)dyi;
-            const float mag = __ldg(t.exp_table + i) * sqrtf(dx * dx + dy * dy);
-            const float ori = __ldg(t.atan2_table + (dyi + 255) * 511 + (dxi + 255));
-            const float ob = scaleO * ori;
-            int oi = (int)floorf(ob);
-            const float of = ob - (float)oi;
-            if (oi < 0) oi += 8;
-            if (oi >= 8) oi -= 8;
-            const int idx = i + 2 * (y >> 3);
-            sm.mag[idx] = mag;
-            sm.of[idx] = of;
-            sm.oi[idx] = (uint8_t)oi;
-        }
-    }
-    __syncwarp();
-    // ---- trilinear histogram (hash_sift.cpp:233-290): lane = cell (rb, cb) in 1..4.  scale is exactly 1/8, so
-    //      bin(r) = (r-16)/8 + 1.5 and the patch rows feeding hist row rb are r in [8rb-12, 8rb+3] (clipped to
-    //      1..30); the table lookups keep the float expression authoritative for membership and weights.
-    {
-        const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
-        const int ybase = 8 * rb - 13, xbase = 8 * cb - 13; // pixel index y = r - 1
-        float* hc = sm.hist + hl * 11;
-        for (int iy = 0; iy < 16; iy++) {
-            const int y = ybase + iy;
-            if (y < 0 || y >= 30) continue;
-            const int ri = bins.bi[y]; const float rf = bins.bf[y];
-            if (ri + 1 != rb && ri + 2 != rb) continue;
-            const bool r_hi = (ri + 2 == rb);
-            const int rowidx = y * 30 + 2 * (y >> 3);
-            for (int ix = 0; ix < 16; ix++) {
-                const int x = xbase + ix;
-                if (x < 0 || x >= 30) continue;
-                const int ci = bins.bi[x]; const float cf = bins.bf[x];
-                if (ci + 1 != cb && ci + 2 != cb) continue;
-                const bool c_hi = (ci + 2 == cb);
-                const int idx = rowidx + x;
-                const float mag = sm.mag[idx];
-                const float of = sm.of[idx];
-                const int oi = sm.oi[idx];
-                // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
-                const float v1 = rf * mag, v0 = mag - v1;
-                const float vr = r_hi ? v1 : v0;
-                const float vc1 = cf * vr, vc0 = vr - vc1;
-                const float vc = c_hi ? vc1 : vc0;
-                const float vo1 = of * vc, vo0 = vc - vo1;
-                hc[oi] += vo0;
-                hc[oi + 1] += vo1;
-            }
-        }
-        __syncwarp();
-        // circular fold (hash_sift.cpp:299-302): bin0 += bin8, bin1 += bin9 (bin 9 is never written: oi <= 7)
-        float* d = sm.desc + hl * 8;
-        d[0] = hc[0] + hc[8];
-        d[1] = hc[1] + hc[9];
-#pragma unroll
-        for (int k = 2; k < 8; k++) d[k] = hc[k];
-    }
-    __syncwarp();
-    // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
-    ef_sift_normalize(sm.desc, hl);
-    for (int i = hl; i < 128; i += 16) sm.desc[i] = fminf(sm.desc[i], 0.2f);
-    __syncwarp();
-    ef_sift_normalize(sm.desc, hl);
-    {
-        unsigned packed[2] = { 0, 0 };
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int q = __float2int_rn(512.f * sm.desc[hl * 8 + j]);
-            packed[j >> 2] |= (unsigned)min(max(q, 0), 255) << (8 * (j & 3));
-        }
-        if (store) reinterpret_cast<uint2*>(out128)[hl] = make_uint2(packed[0], packed[1]);
-    }
-    __syncwarp();
-}
-
-__device__ __forceinline__ void ef_sift_init_bins(EfSiftBins& bins)
-{
-    if (threadIdx.x < 30) { int bi; float bf; ef_sift_bin((int)threadIdx.x + 1, bi, bf); bins.bi[threadIdx.x] = bi; bins.bf[threadIdx.x] = bf; }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(EF_SIFT_KP_PER_CTA * 16) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ EfSiftBins bins;
-    EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
-    ef_sift_init_bins(bins);
-    const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
-    const int first = blockIdx.x * EF_SIFT_KP_PER_CTA + (slot & ~1); // first keypoint of this warp
-    if (first >= job.n) return;
-    const int i = blockIdx.x * EF_SIFT_KP_PER_CTA + slot;
-    const bool valid = i < job.n;
-    const int ii = valid ? i : first;
-    const float4 k = job.kpts[ii];
-    ef_hashsift_one(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[slot], bins, sift128 + (size_t)ii * 128, valid, hl);
-}
-
-void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
-{
-    if (job.n <= 0) return;
-    const size_t smem = sizeof(EfSiftSmem) * EF_SIFT_KP_PER_CTA;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(ef_hashsift_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_KP_PER_CTA * 16, smem, s>>>(job, t, sift128);
-    EF_COUNT_LAUNCH(1);
-}
-
-__global__ void __launch_bounds__(EF_SIFT_KP_PER_CTA * 16) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ EfSiftBins bins;
-    EfSiftSmem* sm = reinterpret_cast<EfSiftSmem*>(s_raw);
-    ef_sift_init_bins(bins);
-    const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
-    const int frame = blockIdx.y;
-    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
-    int level = p.first_level;
-    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].kpt_block_start) level++;
-    const EfLevel& L = p.lv[level];
-    const int nsel = ctr[level].selected;
-    const int first = (blockIdx.x - L.kpt_block_start) * EF_SIFT_KP_PER_CTA + (slot & ~1);
-    if (first >= nsel) return;
-    const int i = (blockIdx.x - L.kpt_block_start) * EF_SIFT_KP_PER_CTA + slot;
-    int offset = 0;
-    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
-    const bool valid = i < nsel && offset + i < p.nfeatures;
-    const int ii = valid ? i : first;
-    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[ii];
-    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
-    // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
-    ef_hashsift_one(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[slot], bins,
-                    sift128 + ((size_t)frame * p.nfeatures + offset + ii) * 128, valid, hl);
-}
-
-void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
-{
-    if (p.total_kpt_blocks <= 0) return;
-    const size_t smem = sizeof(EfSiftSmem) * EF_SIFT_KP_PER_CTA;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(ef_hashsift_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    ef_hashsift_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_SIFT_KP_PER_CTA * 16, smem, s>>>(p, t, sift128);
     EF_COUNT_LAUNCH(1);
 }
 

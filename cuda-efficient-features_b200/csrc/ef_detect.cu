@@ -270,111 +270,161 @@ void ef_launch_score(const EfPipe& p, cudaStream_t s)
 //   * a candidate c is killed by block B iff some pixel of B inside c's disc has a response >= resp_c:
 //     if max(B) < resp_c nothing in B can; if max(B) >= resp_c and argmax(B) is inside the disc it does;
 //     only when max(B) >= resp_c sits OUTSIDE the disc are the pixels of B compared one by one (dense map).
-// One warp per candidate, one lane per neighbouring block ((2K+1)^2 = 25 for r = 15): the 29x29-pixel disc
-// scan of the reference becomes 25 eight-byte loads.  Pure comparisons: results are exact.
+// One CTA per strip of 4 tiles (128x32 pixels = 64 candidates for b = 8), block maxima of the strip and of the K
+// blocks around it staged in shared memory with one global round trip.  Four lanes per candidate share its
+// (2K+1)^2 - 1 neighbours (24 for r = 15): the 29x29-pixel disc scan of the reference becomes 6 eight-byte
+// shared-memory loads per lane.  The rare per-pixel comparisons are queued and done by whole warps afterwards.
+// Pure comparisons: results are exact.
 // Output: one 32-bit survivor word per (tile,row) in tile-major order + per-row survivor counts.
 // =================================================================================================
-#define EF_NMS_MAX_SIDE 20 // blocks per side of the staged neighbourhood: 32/b + 2K <= 20 for every radius in [2, 64]
+#define EF_NMS_RT 4          // tiles per strip
+#define EF_NMS_MAX_BLK 1408  // staged block maxima: (4*32/b + 2K) * (32/b + 2K) <= 1360 for every radius in [2, 64]
+#define EF_NMS_LIST 512
+
+// pixels of block (bx0, by0) inside the disc of (cx, cy) with a response >= r?  q0/qstep: this thread's share of the b*b pixels
+__device__ __forceinline__ bool ef_nms_scan_block(const float* __restrict__ resp, int resp_pitch, int w, int h, int b, int bx0, int by0,
+                                                  int cx, int cy, float r, int r2, int q0, int qstep)
+{
+    bool hit = false;
+    for (int q = q0; q < b * b; q += qstep) {
+        const int gx = bx0 + (q & (b - 1)), gy = by0 + q / b;
+        const int ddx = gx - cx, ddy = gy - cy;
+        if (gx < w && gy < h && ddx * ddx + ddy * ddy < r2 && resp[(size_t)gy * resp_pitch + gx] >= r) hit = true;
+    }
+    return hit;
+}
+
 __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfPipe p)
 {
-    __shared__ unsigned s_mask[EF_TILE];
-    __shared__ EfBlockMax s_blk[EF_NMS_MAX_SIDE * EF_NMS_MAX_SIDE];
+    __shared__ unsigned s_mask[EF_NMS_RT * EF_TILE];
+    __shared__ EfBlockMax s_blk[EF_NMS_MAX_BLK];
+    __shared__ unsigned s_list[EF_NMS_LIST];
+    __shared__ unsigned char s_dead[64];
+    __shared__ int s_nscan;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
-    const int level = ef_find_level(p, blockIdx.x, &EfLevel::tile_start);
+    const int level = ef_find_level(p, blockIdx.x, &EfLevel::strip_start);
     const EfLevel& L = p.lv[level];
-    const int t = blockIdx.x - L.tile_start;
-    const int x0 = (t % L.tiles_x) * EF_TILE, y0 = (t / L.tiles_x) * EF_TILE;
+    const int s = blockIdx.x - L.strip_start;
+    const int ty = s / L.strips_x, tx0 = (s - ty * L.strips_x) * EF_NMS_RT;
+    const int ntx = min(EF_NMS_RT, L.tiles_x - tx0);
+    const int x0 = tx0 * EF_TILE, y0 = ty * EF_TILE;
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
 
     const int b = p.nms_block;
-    if (tid < EF_TILE) s_mask[tid] = 0;
+    if (tid < EF_NMS_RT * EF_TILE) s_mask[tid] = 0;
     if (b == 0) {
         // r^2 <= 1: the disc holds only the pixel itself, every corner survives
         __syncthreads();
-        for (int py = warp; py < EF_TILE; py += 8) {
-            const int gy = y0 + py, gx = x0 + lane;
+        for (int i = warp; i < ntx * EF_TILE; i += 8) {
+            const int gy = y0 + (i & 31), gx = x0 + (i >> 5) * EF_TILE + lane;
             const bool c = gy < L.h && gx < L.w && resp[(size_t)gy * L.resp_pitch + gx] > EF_NEG_INF;
             const unsigned bal = __ballot_sync(0xffffffffu, c);
-            if (lane == 0) s_mask[py] = bal;
+            if (lane == 0) s_mask[i] = bal;
         }
     } else {
-        // stage the block maxima of the tile and of the K blocks around it: one global round trip per CTA
         const EfBlockMax* __restrict__ bmap = reinterpret_cast<const EfBlockMax*>(ef_ws(p, frame, L.blk_off));
-        const int nb = EF_TILE / b, K = p.nms_K, side = nb + 2 * K, r2 = p.nms_r2;
-        const int sbx0 = x0 / b - K, sby0 = y0 / b - K; // block coordinates of s_blk[0]
-        for (int i = tid; i < side * side; i += 256) {
-            const int gby = sby0 + i / side, gbx = sbx0 + i % side;
+        const int lb = 31 - __clz(b), nb = EF_TILE >> lb, lrx = 2 + 5 - lb;   // strip = (4 nb) x nb blocks, 4 nb = 1 << lrx
+        const int K = p.nms_K, r2 = p.nms_r2;
+        const int side_x = (EF_NMS_RT * nb) + 2 * K, side_y = nb + 2 * K;
+        const int sbx0 = (x0 >> lb) - K, sby0 = (y0 >> lb) - K;                // block coordinates of s_blk[0]
+        for (int i = tid; i < side_x * side_y; i += 256) {
+            const int iy = i / side_x, gby = sby0 + iy, gbx = sbx0 + i - iy * side_x;
             EfBlockMax e; e.val = EF_NEG_INF; e.pos = 0;
             if (gbx >= 0 && gby >= 0 && gbx < L.blk_w && gby < L.blk_h) e = bmap[(size_t)gby * L.blk_w + gbx];
             s_blk[i] = e;
         }
-        __syncthreads();
-        const int wside = 2 * K + 1, nnb = wside * wside;
-        for (int c = warp; c < nb * nb; c += 8) {
-            const int ly = c / nb + K, lx = c % nb + K;                       // candidate block in s_blk coordinates
-            const EfBlockMax own = s_blk[ly * side + lx];
-            if (!(own.val > EF_NEG_INF) || (own.pos & 0x80000000u)) continue; // no corner, or a tie inside the block: both die
+        const int wside = 2 * K + 1, nnb = wside * wside, ncand = (EF_NMS_RT * nb) * nb;
+        const int cslot = warp * 8 + (lane >> 2), part = lane & 3;
+        for (int c0 = 0; c0 < ncand; c0 += 64) {
+            if (tid < 64) s_dead[tid] = 0;
+            if (tid == 0) s_nscan = 0;
+            __syncthreads();
+            const int c = c0 + cslot;
+            const int lx = (c & ((1 << lrx) - 1)) + K, ly = (c >> lrx) + K;     // candidate block in s_blk coordinates
+            const int cidx = ly * side_x + lx;
+            EfBlockMax own; own.val = EF_NEG_INF; own.pos = 0;
+            if (c < ncand) own = s_blk[cidx];
+            // only the unique maximum of a block can survive (a tie inside the block kills both)
+            const bool cand = own.val > EF_NEG_INF && !(own.pos & 0x80000000u);
             const float r = own.val;
             const int cx = own.pos & 0xffff, cy = (own.pos >> 16) & 0x7fff;
-            bool dead = false;
-            for (int n0 = 0; n0 < nnb && !dead; n0 += 32) {
-                const int n = n0 + lane;
-                bool kill = false, scan = false;
-                int nbx = 0, nby = 0;
-                if (n < nnb && n != (nnb >> 1)) {                             // the centre of the window is the block itself
-                    const int wy = n / wside, wx = n - wy * wside;
-                    const EfBlockMax e = s_blk[(ly - K + wy) * side + lx - K + wx];
-                    if (e.val >= r) {
-                        const int ex = (int)(e.pos & 0xffff) - cx, ey = (int)((e.pos >> 16) & 0x7fff) - cy;
-                        if (ex * ex + ey * ey < r2) kill = true;
-                        else {
-                            // nearest pixel of the block to the candidate: outside the disc -> the block cannot kill
-                            nbx = sbx0 + lx - K + wx; nby = sby0 + ly - K + wy;
-                            const int bx0 = nbx * b, by0 = nby * b;
-                            const int qx = min(max(cx, bx0), bx0 + b - 1) - cx, qy = min(max(cy, by0), by0 + b - 1) - cy;
-                            scan = qx * qx + qy * qy < r2;
+            const int nbase = (ly - K) * side_x + lx - K;
+            bool kill = false;
+            if (cand) {
+                int wy = part / wside, wx = part - wy * wside;
+                for (int n = part; n < nnb; n += 4) {
+                    if (n != (nnb >> 1)) {                                    // the centre of the window is the block itself
+                        const EfBlockMax e = s_blk[nbase + wy * side_x + wx];
+                        if (e.val >= r) {
+                            const int ex = (int)(e.pos & 0xffff) - cx, ey = (int)((e.pos >> 16) & 0x7fff) - cy;
+                            if (ex * ex + ey * ey < r2) kill = true;
                         }
                     }
-                }
-                if (__any_sync(0xffffffffu, kill)) { dead = true; break; }
-                // rare: max(B) >= r lies outside the disc -> compare the pixels of B inside the disc one by one
-                unsigned todo = __ballot_sync(0xffffffffu, scan);
-                while (todo && !dead) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int px0 = __shfl_sync(0xffffffffu, nbx, src) * b, py0 = __shfl_sync(0xffffffffu, nby, src) * b;
-                    bool k2 = false;
-                    for (int q = lane; q < b * b; q += 32) {
-                        const int gx = px0 + q % b, gy = py0 + q / b;
-                        const int ddx = gx - cx, ddy = gy - cy;
-                        if (gx < L.w && gy < L.h && ddx * ddx + ddy * ddy < r2 && resp[(size_t)gy * L.resp_pitch + gx] >= r) k2 = true;
-                    }
-                    if (__any_sync(0xffffffffu, k2)) dead = true;
+                    wx += 4;
+                    while (wx >= wside) { wx -= wside; wy++; }
                 }
             }
-            if (!dead && lane == 0) atomicOr(&s_mask[cy & 31], 1u << (cx & 31));
+            const unsigned bal = __ballot_sync(0xffffffffu, kill);
+            const bool dead = !cand || ((bal >> (lane & ~3)) & 0xfu) != 0;
+            if (!dead) {
+                // rare: blocks with max(B) >= r whose argmax lies OUTSIDE the disc but which intersect the disc:
+                // their pixels are compared one by one (queued; done inline if the queue is full)
+                int wy = part / wside, wx = part - wy * wside;
+                for (int n = part; n < nnb; n += 4) {
+                    if (n != (nnb >> 1)) {
+                        const int nidx = nbase + wy * side_x + wx;
+                        if (s_blk[nidx].val >= r) {
+                            const int bx0 = (sbx0 + lx - K + wx) << lb, by0 = (sby0 + ly - K + wy) << lb;
+                            const int qx = min(max(cx, bx0), bx0 + b - 1) - cx, qy = min(max(cy, by0), by0 + b - 1) - cy;
+                            if (qx * qx + qy * qy < r2) {                     // nearest pixel of the block is inside the disc
+                                const int slot = atomicAdd(&s_nscan, 1);
+                                if (slot < EF_NMS_LIST) s_list[slot] = (unsigned)cslot | ((unsigned)nidx << 6) | ((unsigned)cidx << 17);
+                                else if (ef_nms_scan_block(resp, L.resp_pitch, L.w, L.h, b, bx0, by0, cx, cy, r, r2, 0, 1)) s_dead[cslot] = 1;
+                            }
+                        }
+                    }
+                    wx += 4;
+                    while (wx >= wside) { wx -= wside; wy++; }
+                }
+            }
+            __syncthreads();
+            const int nscan = min(s_nscan, EF_NMS_LIST);
+            for (int e = warp; e < nscan; e += 8) {
+                const unsigned ent = s_list[e];
+                const int slot = ent & 63, nidx = (ent >> 6) & 2047, oidx = ent >> 17;
+                const EfBlockMax o = s_blk[oidx];
+                const int ny = nidx / side_x, nx = nidx - ny * side_x;
+                const bool hit = ef_nms_scan_block(resp, L.resp_pitch, L.w, L.h, b, (sbx0 + nx) << lb, (sby0 + ny) << lb,
+                                                   o.pos & 0xffff, (o.pos >> 16) & 0x7fff, o.val, r2, lane, 32);
+                if (__any_sync(0xffffffffu, hit) && lane == 0) s_dead[slot] = 1;
+            }
+            __syncthreads();
+            if (!dead && part == 0 && !s_dead[cslot]) atomicOr(&s_mask[((cx >> 5) - tx0) * EF_TILE + (cy & 31)], 1u << (cx & 31));
+            __syncthreads();
         }
     }
     __syncthreads();
 
+    unsigned* mask = reinterpret_cast<unsigned*>(ef_ws(p, frame, L.mask_off));
+    if (tid < ntx * EF_TILE)
+        mask[((size_t)ty * L.tiles_x + tx0 + (tid >> 5)) * EF_TILE + (tid & 31)] = s_mask[tid];
     if (tid < EF_TILE) {
-        unsigned* mask = reinterpret_cast<unsigned*>(ef_ws(p, frame, L.mask_off));
-        const unsigned word = s_mask[tid];
-        mask[(size_t)t * EF_TILE + tid] = word;
+        int cnt = 0;
+        for (int i = 0; i < ntx; i++) cnt += __popc(s_mask[i * EF_TILE + tid]);
         const int gy = y0 + tid;
-        if (word && gy < L.h) {
+        if (cnt && gy < L.h) {
             int* rowcnt = reinterpret_cast<int*>(ef_ws(p, frame, L.rowcnt_off));
-            atomicAdd(&rowcnt[gy], __popc(word));
+            atomicAdd(&rowcnt[gy], cnt);
         }
     }
 }
 
 void ef_launch_nms(const EfPipe& p, cudaStream_t s)
 {
-    if (p.total_tiles <= 0) return;
-    ef_nms_kernel<<<dim3(p.total_tiles, p.nframes), 256, 0, s>>>(p);
+    if (p.total_strips <= 0) return;
+    ef_nms_kernel<<<dim3(p.total_strips, p.nframes), 256, 0, s>>>(p);
     EF_COUNT_LAUNCH(1);
 }
 

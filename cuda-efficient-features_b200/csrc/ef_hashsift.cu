@@ -1,0 +1,263 @@
+// ef_hashsift.cu -- HashSIFT feature kernel (sm_100a): rectified 32x32 patch -> deterministic 4x4x8 gradient
+// histogram -> 128 u8, bit-exact against modules/efficient_features/src/hash_sift.cpp:68-138,150-198,200-331
+// (replaces computePatchSIFTKernel, src/cuda_hash_sift.cu:380-412, whose shared-memory float atomics are not).
+//
+// Compiled with -fmad=false: the CPU reference is a generic x86-64 build without FMA, so every a*b+c below
+// stays two roundings.
+//
+// One HALF-WARP per keypoint (2 keypoints per warp, 4 per 64-thread CTA, ~9.5 KB of shared memory each):
+//   1. (detectAndCompute path) the 48x48-pixel window that bounds the rotated patch is staged in shared memory
+//      with aligned 32-bit loads; the 32x32 bilinear samples (hash_sift.cpp:88-106) then read bytes from it.
+//   2. per gradient pixel (30x30): dx,dy in [-255,255] index ONE 8-byte table entry holding sqrtf(dx^2+dy^2),
+//      the orientation-bin fraction and the bin number (finite-domain tables filled by the host libm, the libm
+//      the CPU reference links); magnitude = expf-table * sqrt.  The 3-bit bin rides in the sign bit of the
+//      magnitude and the two unused top bits of the fraction (< 1), so a pixel record is two floats.
+//   3. trilinear histogram (hash_sift.cpp:233-290): lane c of the half-warp owns histogram cell c (4x4 cells) and
+//      walks the pixels that feed it in raster order, so every accumulator receives exactly the CPU's sequence
+//      of additions.  The cell scale is exactly 1/8, hence the row weight of patch row y is ((y-3) mod 8)/8 and
+//      the rows feeding histogram row rb are 8(rb-2)+3 .. 8(rb-1)+10: two runs of 8 rows (weight w, then 1-w) -- the
+//      same for columns -- which makes the loop nest static.  Accumulators live in shared memory as
+//      hist[bin][lane]: bank = lane, conflict-free for any bin; pixel records are skewed (y*30 + x + 2*(y>>3)) so
+//      that the 16 cells of one keypoint hit 16 distinct even banks and the second keypoint of the warp (array
+//      base an odd number of words further) the odd ones.
+//   4. fold bins 8 -> 0, L2-normalise (sequential sum), clip 0.2, renormalise, x512 -> u8 (hash_sift.cpp:293-330).
+#include "ef_common.cuh"
+#include "ef_libm_f32.cuh"
+
+#include <cfloat>
+
+#define EF_SIFT_WARPS 2                 // per CTA: 4 keypoints
+#define EF_SIFT_KP_PER_CTA (2 * EF_SIFT_WARPS)
+#define EF_SIFT_REC 913                 // odd: the second keypoint of a warp lands on the other bank parity
+#define EF_SIFT_WIN 48                  // staged window edge (pixels); every sample of a size-31 patch lies in [k-22, k+22]
+#define EF_SIFT_WIN_WORDS 13            // 48 pixels + up to 3 alignment bytes
+#define EF_SIFT_WIN_PITCH (4 * EF_SIFT_WIN_WORDS)
+
+struct EfSiftWarpSmem {                 // per warp = 2 keypoints
+    float hist[9 * 32];                 // [bin 0..8][lane]
+    float magp[2][EF_SIFT_REC];         // magnitude, sign bit = bin bit 2; phase 1 aliases the staging window here
+    float ofp[2][EF_SIFT_REC];          // orientation fraction, bits 31:30 = bin bits 1:0
+    float desc[2][128];
+    uint8_t patch[2][32 * 32];
+};
+static_assert(EF_SIFT_WIN * EF_SIFT_WIN_WORDS <= EF_SIFT_REC, "staging window must fit the record array it aliases");
+
+// normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
+__device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
+{
+    float sum = 0.f;
+    const float4* d4 = reinterpret_cast<const float4*>(d);
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+        const float4 v = d4[i];
+        sum += v.x * v.x; sum += v.y * v.y; sum += v.z * v.z; sum += v.w * v.w;
+    }
+    const float nrm = fmaxf(sqrtf(sum), FLT_EPSILON);
+    const float scale = 1.f / nrm;
+    __syncwarp();
+    for (int i = hl; i < 128; i += 16) d[i] *= scale;
+    __syncwarp();
+}
+
+// All 32 lanes call this; lanes 0-15 work on keypoint slot 0 of the warp, lanes 16-31 on slot 1.
+// STAGED: integer keypoint, size 31, scale 1 (detectAndCompute path): window staging; image base and pitch 4-byte aligned.
+template <bool STAGED>
+__device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
+                                                float kx, float ky, float size, float angle, float croppingScale,
+                                                const EfHashSiftTables& t, EfSiftWarpSmem& sm, uint8_t* out128, bool store)
+{
+    const int lane = threadIdx.x & 31, hl = lane & 15, k = lane >> 4;
+    uint8_t* patch = sm.patch[k];
+    // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
+    {
+        const float PI_1_0F = 3.14159274f;
+        const float s = croppingScale * size / (0.5f * (float)(32 + 32));
+        const float theta = PI_1_0F * angle / 180;
+        // cosf/sinf: the host libm's algorithm, bit for bit (ef_libm_f32.cuh)
+        const float cost = s * (angle >= 0 ? ef_libm::cosf_glibc(theta) : 1.f);
+        const float sint = s * (angle >= 0 ? ef_libm::sinf_glibc(theta) : 0.f);
+        const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
+        const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
+        const uint8_t* base = img;
+        int bpitch = pitch, ox = 0, oy = 0;
+        if (STAGED) {
+            const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - EF_SIFT_WIN / 2;
+            const int gx0 = wx0 & ~3;
+            unsigned* win = reinterpret_cast<unsigned*>(sm.magp[k]);
+            if (hl < EF_SIFT_WIN_WORDS) {
+                const int gxw = gx0 + 4 * hl;
+                const bool colok = gxw >= 0 && gxw + 3 < pitch;
+#pragma unroll 8
+                for (int row = 0; row < EF_SIFT_WIN; row++) {
+                    const int gy = wy0 + row;
+                    unsigned v = 0;
+                    if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gxw));
+                    win[row * EF_SIFT_WIN_WORDS + hl] = v;
+                }
+            }
+            __syncwarp();
+            base = reinterpret_cast<const uint8_t*>(win); bpitch = EF_SIFT_WIN_PITCH; ox = gx0; oy = wy0;
+        }
+        const float cx0 = M00 * (float)hl, cx1 = M00 * (float)(hl + 16);
+        const float cy0 = M10 * (float)hl, cy1 = M10 * (float)(hl + 16);
+        for (int y = 0; y < 32; y++) {
+            const float ru = M01 * (float)y, rv = M11 * (float)y;
+#pragma unroll
+            for (int xx = 0; xx < 2; xx++) {
+                const float u = ((xx ? cx1 : cx0) + ru) + M02;
+                const float v = ((xx ? cy1 : cy0) + rv) + M12;
+                uint8_t dstVal = 0;
+                const int ui = (int)floorf(u);
+                const int vi = (int)floorf(v);
+                if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
+                    const uint8_t* q = base + (vi - oy) * bpitch + (ui - ox);
+                    const float du = u - (float)ui;
+                    const float dv = v - (float)vi;
+                    const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
+                    const float tmp1 = (1 - du) * (float)q[bpitch] + du * (float)q[bpitch + 1];
+                    const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
+                    dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
+                }
+                patch[y * 32 + hl + 16 * xx] = dstVal;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu)
+    {
+        float* magp = sm.magp[k];
+        float* ofp = sm.ofp[k];
+        int x = hl, y = 0;
+        for (int i = hl; i < 900; i += 16) {
+            const uint8_t* c = patch + (y + 1) * 32 + x + 1;
+            const int dxi = (int)c[1] - (int)c[-1];
+            const int dyi = (int)c[-32] - (int)c[32];
+            const float2 e = __ldg(t.grad_table + (dyi + 255) * 511 + (dxi + 255));
+            const int idx = i + 2 * (y >> 3);
+            magp[idx] = __ldg(t.exp_table + i) * e.x;
+            ofp[idx] = e.y;
+            x += 16;
+            if (x >= 30) { x -= 30; y++; }
+        }
+    }
+    for (int b = 0; b < 9; b++) sm.hist[b * 32 + lane] = 0.f;
+    __syncwarp();
+    // ---- trilinear histogram (hash_sift.cpp:233-290); cell (rb, cb) in 1..4
+    {
+        const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
+        const float* mp = sm.magp[k];
+        const unsigned* op = reinterpret_cast<const unsigned*>(sm.ofp[k]);
+        float* hc = sm.hist + lane;
+        const int xb = 8 * (cb - 2) + 3;
+#pragma unroll
+        for (int rseg = 0; rseg < 2; rseg++) {
+            for (int iy = 0; iy < 8; iy++) {
+                const int y = 8 * (rb - 2 + rseg) + 3 + iy;
+                const bool rowok = (unsigned)y < 30u;
+                const float rf = 0.125f * (float)iy;
+                const int rowidx = y * 30 + 2 * (y >> 3) + xb;
+#pragma unroll
+                for (int cseg = 0; cseg < 2; cseg++) {
+#pragma unroll
+                    for (int ix = 0; ix < 8; ix++) {
+                        const int xo = 8 * cseg + ix;
+                        if (rowok && (unsigned)(xb + xo) < 30u) {
+                            const float mg = mp[rowidx + xo];
+                            const unsigned ob = op[rowidx + xo];
+                            const float mag = fabsf(mg);
+                            const unsigned oi = (ob >> 30) | ((__float_as_uint(mg) >> 31) << 2);
+                            const float of = __uint_as_float(ob & 0x3fffffffu);
+                            // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
+                            const float v1 = rf * mag;
+                            const float vr = rseg == 0 ? v1 : mag - v1;
+                            const float c1 = (0.125f * (float)ix) * vr;
+                            const float vc = cseg == 0 ? c1 : vr - c1;
+                            const float vo1 = of * vc, vo0 = vc - vo1;
+                            float* h0 = hc + oi * 32;
+                            const float a0 = h0[0], a1 = h0[32];
+                            h0[0] = a0 + vo0;
+                            h0[32] = a1 + vo1;
+                        }
+                    }
+                }
+            }
+        }
+        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: the bin number is <= 7)
+        float* d = sm.desc[k] + hl * 8;
+        d[0] = hc[0] + hc[8 * 32];
+#pragma unroll
+        for (int b = 1; b < 8; b++) d[b] = hc[b * 32];
+    }
+    __syncwarp();
+    // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
+    float* desc = sm.desc[k];
+    ef_sift_normalize(desc, hl);
+    for (int i = hl; i < 128; i += 16) desc[i] = fminf(desc[i], 0.2f);
+    __syncwarp();
+    ef_sift_normalize(desc, hl);
+    {
+        unsigned packed[2] = { 0, 0 };
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int q = __float2int_rn(512.f * desc[hl * 8 + j]);
+            packed[j >> 2] |= (unsigned)min(max(q, 0), 255) << (8 * (j & 3));
+        }
+        if (store) reinterpret_cast<uint2*>(out128)[hl] = make_uint2(packed[0], packed[1]);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    EfSiftWarpSmem* sm = reinterpret_cast<EfSiftWarpSmem*>(s_raw);
+    const int slot = threadIdx.x >> 4, warp = threadIdx.x >> 5;
+    const int first = blockIdx.x * EF_SIFT_KP_PER_CTA + (slot & ~1); // first keypoint of this warp
+    if (first >= job.n) return;
+    const int i = blockIdx.x * EF_SIFT_KP_PER_CTA + slot;
+    const bool valid = i < job.n;
+    const int ii = valid ? i : first;
+    const float4 k = job.kpts[ii];
+    ef_hashsift_one<false>(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)ii * 128, valid);
+}
+
+void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
+{
+    if (job.n <= 0) return;
+    const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
+    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_WARPS * 32, smem, s>>>(job, t, sift128);
+    EF_COUNT_LAUNCH(1);
+}
+
+__global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    EfSiftWarpSmem* sm = reinterpret_cast<EfSiftWarpSmem*>(s_raw);
+    const int slot = threadIdx.x >> 4, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.y;
+    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    int level = p.first_level;
+    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].sift_block_start) level++;
+    const EfLevel& L = p.lv[level];
+    const int nsel = ctr[level].selected;
+    const int first = (blockIdx.x - L.sift_block_start) * EF_SIFT_KP_PER_CTA + (slot & ~1);
+    if (first >= nsel) return;
+    const int i = (blockIdx.x - L.sift_block_start) * EF_SIFT_KP_PER_CTA + slot;
+    int offset = 0;
+    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
+    const bool valid = i < nsel && offset + i < p.nfeatures;
+    const int ii = valid ? i : first;
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[ii];
+    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
+    // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
+    ef_hashsift_one<true>(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],
+                          sift128 + ((size_t)frame * p.nfeatures + offset + ii) * 128, valid);
+}
+
+void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
+{
+    if (p.total_sift_blocks <= 0) return;
+    const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
+    ef_hashsift_pipe_kernel<<<dim3(p.total_sift_blocks, p.nframes), EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128);
+    EF_COUNT_LAUNCH(1);
+}
