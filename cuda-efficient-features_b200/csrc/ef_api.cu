@@ -409,7 +409,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
             bands += L.tiles_y;
             kblocks += ef_div_up(std::min(L.quota, p.nfeatures), 8);
             sblocks += ef_div_up(std::min(L.quota, p.nfeatures), 4);
-            btiles += L.blur_tiles_x * ef_div_up(L.h, 32);
+            btiles += L.blur_tiles_x * ef_div_up(L.h, 64);
         }
     }
     P.total_tiles = tiles; P.total_blur_tiles = btiles; P.total_bands = bands; P.total_kpt_blocks = kblocks; P.total_sift_blocks = sblocks; P.total_strips = strips;

@@ -36,7 +36,7 @@ struct EfLevel {
     int blk_w, blk_h;   // dimensions of the NMS block-maximum map (ceil(w / nms_block), ceil(h / nms_block))
     int tile_start;     // first tile index of this level in the all-level tile table
     int strips_x, strip_start; // NMS strips of 4 tiles per tile row; first strip index of this level
-    int blur_tile_start, blur_tiles_x; // 64x32 blur tiles
+    int blur_tile_start, blur_tiles_x; // 64x64 blur tiles
     int band_start;     // first 32-row band index of this level
     int quota;          // nfeaturesPerLevel_[s]
     int surv_cap;       // capacity of the survivor list

@@ -15,6 +15,8 @@
 // stage (tile tables in EfPipe), except the pyramid chain whose level s needs level s-1.
 #include "ef_common.cuh"
 
+#include <cuda_fp16.h>
+
 // =================================================================================================
 // pyramid: bilinear x(1/scaleFactor) chain, one launch per level over the whole batch
 // =================================================================================================
@@ -72,20 +74,18 @@ void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
 
 // =================================================================================================
 // score: FAST-9/16 inside the 15-px border + Harris at every corner -> dense response map
+//
+// 32x32-pixel tile + 4-pixel halo per CTA.  Pixels are converted once to fp16 (exact for 0..255) and kept twice in shared
+// memory -- s_h0[r][c] = pixel c, s_h1[r][c] = pixel c+1 -- so that the pair (c, c+1) is an aligned 32-bit word for even AND
+// odd c: the FAST ring test and the Sobel gradients then run two pixels per instruction on half2 (HSET2 compare masks,
+// HADD2/HFMA2; every intermediate is an integer below 2048, hence exact).
 // =================================================================================================
 #define SC_HALO 4
-#define SC_W (EF_TILE + 2 * SC_HALO) // 40
-#define SC_G (EF_TILE + 6)           // 38: gradient region [-3, 34]
-
-__device__ __forceinline__ bool ef_has_arc9(unsigned m)
-{
-    const unsigned mm = m | (m << 16);
-    unsigned a = mm & (mm >> 1);
-    a &= a >> 2;
-    a &= a >> 4;
-    a &= mm >> 8;
-    return (a & 0xffffu) != 0;
-}
+#define SC_ROWS (EF_TILE + 2 * SC_HALO)  // 40
+#define SC_PAD 4                         // halves left of tile-local column 0
+#define SC_HP 48                         // halves per row = 24 words: 4 consecutive rows x 8 words hit 32 distinct banks
+#define SC_HW (SC_HP / 2)
+#define SC_GROWS (EF_TILE + 6)           // 38 gradient rows (tile-local rows 1..38)
 
 __device__ __forceinline__ int ef_find_level(const EfPipe& p, int idx, int EfLevel::*start)
 {
@@ -94,79 +94,145 @@ __device__ __forceinline__ int ef_find_level(const EfPipe& p, int idx, int EfLev
     return level;
 }
 
+// rotate both 16-bit halves of m left by S
+template <int S> __device__ __forceinline__ unsigned ef_rot16x2(unsigned m)
+{
+    constexpr unsigned A = ((0xffffu << S) & 0xffffu) * 0x10001u;
+    return ((m << S) & A) | ((m >> (16 - S)) & ~A);
+}
+// per 16-bit half: bit i set iff bits i, i-1, ..., i-8 (circular) of that half are all set -> non-zero half <=> 9-arc
+__device__ __forceinline__ unsigned ef_arc9x2(unsigned m)
+{
+    unsigned r = m & ef_rot16x2<1>(m);
+    r &= ef_rot16x2<2>(r);
+    r &= ef_rot16x2<4>(r);
+    return r & __byte_perm(m, 0, 0x2301);
+}
+
 __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ EfPipe p)
 {
-    __shared__ uint8_t s_img[SC_W][SC_W + 8];
-    __shared__ float2 s_grad[SC_G][SC_G + 1];
+    __shared__ __align__(16) unsigned s_h0[SC_ROWS][SC_HW];
+    __shared__ __align__(16) unsigned s_h1[SC_ROWS][SC_HW];
+    __shared__ __align__(16) float2 s_grad[SC_GROWS][SC_ROWS];
     __shared__ __align__(16) float s_resp[EF_TILE][EF_TILE];
     __shared__ unsigned short s_list[EF_TILE * EF_TILE];
     __shared__ int s_n;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.tile_start;
-    const int x0 = (t % L.tiles_x) * EF_TILE, y0 = (t / L.tiles_x) * EF_TILE;
+    const int ty = t / L.tiles_x;
+    const int x0 = (t - ty * L.tiles_x) * EF_TILE, y0 = ty * EF_TILE;
 
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0;
 
+    // ---- tile + halo -> fp16 pairs.  Pixels outside the image read as 0: no corner lies within 15 px of the border and
+    //      neither the ring (3) nor the Harris window (4) reaches them.
     if (tid == 0) s_n = 0;
-    for (int i = tid; i < SC_W * SC_W; i += 256) {
-        const int ly = i / SC_W, lx = i - ly * SC_W;
-        const int gy = min(max(y0 - SC_HALO + ly, 0), L.h - 1);
-        const int gx = min(max(x0 - SC_HALO + lx, 0), L.w - 1);
-        s_img[ly][lx] = img[(size_t)gy * pitch + gx];
+    for (int i = tid; i < SC_ROWS * 10; i += 256) {
+        const int row = i / 10, wx = i - row * 10;
+        const int gy = y0 - SC_HALO + row, gx = x0 - SC_HALO + 4 * wx;
+        unsigned word = 0;
+        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.w) {
+            const uint8_t* rp = img + (size_t)gy * pitch + gx;
+            if (aligned && gx + 3 < L.w) word = *reinterpret_cast<const unsigned*>(rp);
+            else {
+                word = rp[0];
+                if (gx + 1 < L.w) word |= (unsigned)rp[1] << 8;
+                if (gx + 2 < L.w) word |= (unsigned)rp[2] << 16;
+                if (gx + 3 < L.w) word |= (unsigned)rp[3] << 24;
+            }
+        }
+        // bytes -> halves: 0x6400 | b is the half 1024 + b; subtracting 1024 is exact
+        const unsigned k1024 = 0x64006400u;
+        unsigned h01 = __byte_perm(word, 0x64646464u, 0x4140), h23 = __byte_perm(word, 0x64646464u, 0x4342);
+        __half2 a = __hsub2(*reinterpret_cast<__half2*>(&h01), *reinterpret_cast<const __half2*>(&k1024));
+        __half2 b = __hsub2(*reinterpret_cast<__half2*>(&h23), *reinterpret_cast<const __half2*>(&k1024));
+        uint2 o;
+        o.x = *reinterpret_cast<unsigned*>(&a); o.y = *reinterpret_cast<unsigned*>(&b);
+        *reinterpret_cast<uint2*>(&s_h0[row][SC_PAD / 2 + 2 * wx]) = o;
+    }
+    __syncthreads();
+    // shifted copy: pair j of s_h1 = (pixel j+1, pixel j+2), j = -2, 0, ..., 38
+    for (int i = tid; i < SC_ROWS * 21; i += 256) {
+        const int row = i / 21, jj = i - row * 21;      // pair index jj <-> j = 2*jj - 2 <-> word SC_PAD/2 + jj - 1
+        const unsigned A = s_h0[row][SC_PAD / 2 + jj - 1], B = s_h0[row][SC_PAD / 2 + jj];
+        s_h1[row][SC_PAD / 2 + jj - 1] = __byte_perm(A, B, 0x5432);
     }
     __syncthreads();
 
-    // ---- FAST-9/16 (cuda_fast.cu:36-40,162-166: mask1 = darker, mask2 = brighter, >= 9 contiguous)
-    const int tx = tid & 31, ty = tid >> 5, lane = tx;
-    const int th = p.fast_threshold;
+    // ---- FAST-9/16 (cuda_fast.cu:36-40,162-166: mask1 = darker, mask2 = brighter, >= 9 contiguous), two pixels per thread
+    {
+        const unsigned thu = (unsigned)__half_as_ushort(__int2half_rn(p.fast_threshold)) * 0x10001u;
+        const __half2 th2 = *reinterpret_cast<const __half2*>(&thu);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int py = ty + 8 * i;
-        const int gx = x0 + tx, gy = y0 + py;
-        bool corner = false;
-        if (gx >= EF_HALF_PATCH && gx < L.w - EF_HALF_PATCH && gy >= EF_HALF_PATCH && gy < L.h - EF_HALF_PATCH) {
-            const int cy = py + SC_HALO, cx = tx + SC_HALO;
-            const int v = s_img[cy][cx];
-            const int lo = v - th, hi = v + th;
+        for (int pass = 0; pass < 2; pass++) {
+            const int task = warp + 8 * pass;
+            const int py = 4 * (task >> 1) + (lane >> 3), px = 16 * (task & 1) + 2 * (lane & 7);
+            const unsigned* r0 = &s_h0[py + SC_HALO][(SC_PAD + SC_HALO + px) / 2];
+            const unsigned* r1 = &s_h1[py + SC_HALO][(SC_PAD + SC_HALO + px) / 2];
+            const unsigned cu = r0[0];
+            const __half2 c2 = *reinterpret_cast<const __half2*>(&cu);
+            const __half2 lo = __hsub2(c2, th2), hi = __hadd2(c2, th2);
             unsigned dark = 0, bright = 0;
-#define EF_RING(k, dy, dx) { const int q = s_img[cy + (dy)][cx + (dx)]; dark |= (unsigned)(q < lo) << (k); bright |= (unsigned)(q > hi) << (k); }
+            // ring pixel (dy, dx) of both pixels of the pair: even dx -> s_h0 word dx/2, odd dx -> s_h1 word (dx-1)/2
+#define EF_RING(k, dy, dx) { const unsigned qu = ((dx) & 1) ? r1[(dy) * SC_HW + ((dx) - 1) / 2] : r0[(dy) * SC_HW + (dx) / 2]; \
+                             const __half2 q2 = *reinterpret_cast<const __half2*>(&qu); \
+                             dark |= __hlt2_mask(q2, lo) & (0x10001u << (k)); bright |= __hgt2_mask(q2, hi) & (0x10001u << (k)); }
             EF_RING(0, 3, 0) EF_RING(8, -3, 0) EF_RING(4, 0, 3) EF_RING(12, 0, -3)
-            if ((dark | bright) != 0) { // at least one of the 4 compass pixels differs, else no 9-arc is possible
+            unsigned arc = 0;
+            if (__any_sync(0xffffffffu, (dark | bright) != 0)) { // no 9-arc without one of the 4 compass pixels
                 EF_RING(1, 3, 1) EF_RING(2, 2, 2) EF_RING(3, 1, 3) EF_RING(5, -1, 3) EF_RING(6, -2, 2) EF_RING(7, -3, 1)
                 EF_RING(9, -3, -1) EF_RING(10, -2, -2) EF_RING(11, -1, -3) EF_RING(13, 1, -3) EF_RING(14, 2, -2) EF_RING(15, 3, -1)
-                corner = ef_has_arc9(dark) || ef_has_arc9(bright);
+                arc = ef_arc9x2(dark) | ef_arc9x2(bright);
             }
 #undef EF_RING
+            const int gx = x0 + px, gy = y0 + py;
+            const bool rowok = gy >= EF_HALF_PATCH && gy < L.h - EF_HALF_PATCH;
+            const bool c0 = rowok && (arc & 0xffffu) != 0 && gx >= EF_HALF_PATCH && gx < L.w - EF_HALF_PATCH;
+            const bool c1 = rowok && (arc >> 16) != 0 && gx + 1 >= EF_HALF_PATCH && gx + 1 < L.w - EF_HALF_PATCH;
+            *reinterpret_cast<float2*>(&s_resp[py][px]) = make_float2(EF_NEG_INF, EF_NEG_INF);
+            const unsigned bal0 = __ballot_sync(0xffffffffu, c0), bal1 = __ballot_sync(0xffffffffu, c1);
+            const int n0 = __popc(bal0), cnt = n0 + __popc(bal1);
+            int base = 0;
+            if (lane == 0 && cnt) base = atomicAdd(&s_n, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (c0) s_list[base + __popc(bal0 & lt)] = (unsigned short)((py << 5) | px);
+            if (c1) s_list[base + n0 + __popc(bal1 & lt)] = (unsigned short)((py << 5) | (px + 1));
         }
-        s_resp[py][tx] = EF_NEG_INF;
-        const unsigned bal = __ballot_sync(0xffffffffu, corner);
-        const int cnt = __popc(bal);
-        int base = 0;
-        if (lane == 0 && cnt) base = atomicAdd(&s_n, cnt);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (corner) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((py << 5) | tx);
     }
     __syncthreads();
     const int n = s_n;
 
     if (n > 0) {
-        // ---- Sobel gradients of the tile (+3 halo), cuda_efficient_features.cu:116-128
+        // ---- Sobel gradients of tile-local rows/columns 1..38 (cuda_efficient_features.cu:116-128), two pixels per thread:
+        //      dx = colsum(x+1) - colsum(x-1), colsum = v(y-1) + 2 v(y) + v(y+1); dy likewise with rows
         const float SCALE = 1.f / (4 * 7 * 255);
-        for (int i = tid; i < SC_G * SC_G; i += 256) {
-            const int gyl = i / SC_G, gxl = i - gyl * SC_G;
-            const int ly = gyl + 1, lx = gxl + 1;
-            const int v00 = s_img[ly - 1][lx - 1], v01 = s_img[ly - 1][lx], v02 = s_img[ly - 1][lx + 1];
-            const int v10 = s_img[ly][lx - 1], v12 = s_img[ly][lx + 1];
-            const int v20 = s_img[ly + 1][lx - 1], v21 = s_img[ly + 1][lx], v22 = s_img[ly + 1][lx + 1];
-            float2 g;
-            g.x = SCALE * (float)((v02 + 2 * v12 + v22) - (v00 + 2 * v10 + v20));
-            g.y = SCALE * (float)((v20 + 2 * v21 + v22) - (v00 + 2 * v01 + v02));
-            s_grad[gyl][gxl] = g;
+        const unsigned twou = 0x40004000u;
+        const __half2 two = *reinterpret_cast<const __half2*>(&twou);
+        for (int i = tid; i < SC_GROWS * 20; i += 256) {
+            const int row = i / 20, pr = i - row * 20;      // gradient row `row` <-> tile-local row row+1; pair of columns 2pr, 2pr+1
+            const unsigned* hm = &s_h0[row][SC_PAD / 2 + pr];
+            const unsigned* sm1 = &s_h1[row][SC_PAD / 2 + pr];
+#define H2(u) (*reinterpret_cast<const __half2*>(&(u)))
+            const unsigned am = sm1[-1], bm = hm[0], cm = sm1[0];                                     // row-1: columns x-1, x, x+1
+            const unsigned a0 = sm1[SC_HW - 1], c0 = sm1[SC_HW];                                     // row
+            const unsigned ap = sm1[2 * SC_HW - 1], bp = hm[2 * SC_HW], cp = sm1[2 * SC_HW];          // row+1
+            const __half2 right = __hfma2(two, H2(c0), __hadd2(H2(cm), H2(cp)));
+            const __half2 left = __hfma2(two, H2(a0), __hadd2(H2(am), H2(ap)));
+            const __half2 down = __hfma2(two, H2(bp), __hadd2(H2(ap), H2(cp)));
+            const __half2 up = __hfma2(two, H2(bm), __hadd2(H2(am), H2(cm)));
+#undef H2
+            const __half2 dx2 = __hsub2(right, left), dy2 = __hsub2(down, up);
+            float4 g;
+            g.x = SCALE * __low2float(dx2); g.y = SCALE * __low2float(dy2);
+            g.z = SCALE * __high2float(dx2); g.w = SCALE * __high2float(dy2);
+            *reinterpret_cast<float4*>(&s_grad[row][2 * pr]) = g;
         }
         __syncthreads();
         // ---- Harris, raster order over the 7x7 block with the reference's contraction
@@ -178,7 +244,7 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             for (int iy = 0; iy < 7; iy++) {
 #pragma unroll
                 for (int ix = 0; ix < 7; ix++) {
-                    const float2 g = s_grad[cy + iy][cx + ix];
+                    const float2 g = s_grad[cy + iy][cx + 1 + ix];
                     sxx = fmaf(g.x, g.x, sxx);
                     sxy = fmaf(g.x, g.y, sxy);
                     syy = fmaf(g.y, g.y, syy);
@@ -722,56 +788,96 @@ void ef_launch_angle_pack(const EfPipe& p, cudaStream_t s)
 
 // =================================================================================================
 // blur: separable 7-tap Gaussian (sigma 2), float row pass then column pass, BORDER_REFLECT_101,
-// u8 -> u8 with round-half-even.  64x32 tile, all levels in one launch.
+// u8 -> u8 with round-half-even.  64x64 tile, all levels in one launch.
+//   load : 70 rows x 72 bytes as aligned 32-bit words (byte-wise with reflection only in tiles that touch the left/right edge)
+//   rows : one thread = 4 adjacent outputs of a row: 3 word loads, 10 byte->float conversions on the FMA pipe
+//          (0x4B0000bb is the float 2^23 + b; subtracting 2^23 is exact), 28 FFMA, one 16-byte store
+//   cols : one thread = 4x4 outputs: 10 16-byte loads, 112 FFMA, 4 packed 32-bit stores
 // =================================================================================================
 #define BL_TW 64
-#define BL_TH 32
+#define BL_TH 64
+#define BL_IW 18 // words per staged input row: columns x0-4 .. x0+67
+__device__ __forceinline__ float ef_byte_to_float(unsigned word, int i)
+{
+    const unsigned m = __byte_perm(word, 0x4B000000u, 0x7540 + i);
+    return __uint_as_float(m) - 8388608.f;
+}
+
 __global__ void __launch_bounds__(256) ef_blur_kernel(const __grid_constant__ EfPipe p)
 {
-    __shared__ uint8_t s_in[BL_TH + 6][BL_TW + 8];
-    __shared__ float s_row[BL_TH + 6][BL_TW];
+    __shared__ unsigned s_in[BL_TH + 6][BL_IW];
+    __shared__ __align__(16) float s_row[BL_TH + 6][BL_TW];
 
-    const float taps[7] = { __uint_as_float(0x3d8fafb1u), __uint_as_float(0x3e06387eu), __uint_as_float(0x3e434a39u),
-                            __uint_as_float(0x3e5d4ae0u), __uint_as_float(0x3e434a39u), __uint_as_float(0x3e06387eu),
-                            __uint_as_float(0x3d8fafb1u) };
+    const float t0 = __uint_as_float(0x3d8fafb1u), t1 = __uint_as_float(0x3e06387eu), t2 = __uint_as_float(0x3e434a39u),
+                t3 = __uint_as_float(0x3e5d4ae0u);
+    const float taps[7] = { t0, t1, t2, t3, t2, t1, t0 };
     const int tid = threadIdx.x;
     const int frame = blockIdx.y;
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::blur_tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.blur_tile_start;
-    const int x0 = (t % L.blur_tiles_x) * BL_TW, y0 = (t / L.blur_tiles_x) * BL_TH;
+    const int tyi = t / L.blur_tiles_x;
+    const int x0 = (t - tyi * L.blur_tiles_x) * BL_TW, y0 = tyi * BL_TH;
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
+    const bool fast = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0 && x0 >= 4 && x0 + BL_TW + 4 <= L.w;
 
-    for (int i = tid; i < (BL_TH + 6) * (BL_TW + 6); i += 256) {
-        const int ly = i / (BL_TW + 6), lx = i - ly * (BL_TW + 6);
+    for (int i = tid; i < (BL_TH + 6) * BL_IW; i += 256) {
+        const int ly = i / BL_IW, wx = i - ly * BL_IW;
         const int gy = ef_reflect101(min(y0 - 3 + ly, L.h + 2), L.h);
-        const int gx = ef_reflect101(min(x0 - 3 + lx, L.w + 2), L.w);
-        s_in[ly][lx] = img[(size_t)gy * pitch + gx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += 256) {
-        const int ly = i / BL_TW, lx = i - ly * BL_TW;
-        float sum = 0.f;
+        const uint8_t* rp = img + (size_t)gy * pitch;
+        const int gx = x0 - 4 + 4 * wx;
+        unsigned word;
+        if (fast) word = *reinterpret_cast<const unsigned*>(rp + gx);
+        else {
+            word = 0;
 #pragma unroll
-        for (int k = 0; k < 7; k++) sum = fmaf((float)s_in[ly][lx + k], taps[k], sum);
-        s_row[ly][lx] = sum;
+            for (int j = 0; j < 4; j++) word |= (unsigned)rp[ef_reflect101(min(gx + j, L.w + 2), L.w)] << (8 * j);
+        }
+        s_in[ly][wx] = word;
     }
     __syncthreads();
-    uint8_t* out = ef_ws(p, frame, L.blur_off);
-    for (int i = tid; i < BL_TH * BL_TW / 4; i += 256) {
-        const int ly = i / (BL_TW / 4), lx = (i - ly * (BL_TW / 4)) * 4;
-        const int gy = y0 + ly, gx = x0 + lx;
-        if (gy >= L.h || gx >= L.w) continue;
-        unsigned packed = 0;
+    // row pass: output columns 4c .. 4c+3 need input columns 4c-3 .. 4c+6 = staged bytes 4c+1 .. 4c+10
+    for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4); i += 256) {
+        const int ly = i >> 4, c = i & 15;
+        const unsigned w0 = s_in[ly][c], w1 = s_in[ly][c + 1], w2 = s_in[ly][c + 2];
+        float f[10];
+        f[0] = ef_byte_to_float(w0, 1); f[1] = ef_byte_to_float(w0, 2); f[2] = ef_byte_to_float(w0, 3);
+        f[3] = ef_byte_to_float(w1, 0); f[4] = ef_byte_to_float(w1, 1); f[5] = ef_byte_to_float(w1, 2); f[6] = ef_byte_to_float(w1, 3);
+        f[7] = ef_byte_to_float(w2, 0); f[8] = ef_byte_to_float(w2, 1); f[9] = ef_byte_to_float(w2, 2);
+        float o[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 7; k++) sum = fmaf(s_row[ly + k][lx + j], taps[k], sum);
-            packed |= ef_sat_u8_rne(sum) << (8 * j);
+            for (int k = 0; k < 7; k++) sum = fmaf(f[j + k], taps[k], sum);
+            o[j] = sum;
         }
-        *reinterpret_cast<unsigned*>(out + (size_t)gy * L.blur_pitch + gx) = packed;
+        *reinterpret_cast<float4*>(&s_row[ly][4 * c]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // column pass: 4 columns x 4 rows per thread
+    {
+        const int c = tid & 15, rg = tid >> 4;
+        const int gx = x0 + 4 * c;
+        float4 r[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) r[k] = *reinterpret_cast<const float4*>(&s_row[4 * rg + k][4 * c]);
+        uint8_t* out = ef_ws(p, frame, L.blur_off);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                sum.x = fmaf(r[j + k].x, taps[k], sum.x); sum.y = fmaf(r[j + k].y, taps[k], sum.y);
+                sum.z = fmaf(r[j + k].z, taps[k], sum.z); sum.w = fmaf(r[j + k].w, taps[k], sum.w);
+            }
+            const int gy = y0 + 4 * rg + j;
+            if (gy < L.h && gx < L.w) {
+                const unsigned packed = ef_sat_u8_rne(sum.x) | (ef_sat_u8_rne(sum.y) << 8) | (ef_sat_u8_rne(sum.z) << 16) | (ef_sat_u8_rne(sum.w) << 24);
+                *reinterpret_cast<unsigned*>(out + (size_t)gy * L.blur_pitch + gx) = packed; // blur_pitch is a multiple of 128
+            }
+        }
     }
 }
 

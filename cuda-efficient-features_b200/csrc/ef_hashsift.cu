@@ -28,19 +28,21 @@
 
 #define EF_SIFT_WARPS 2                 // per CTA: 4 keypoints
 #define EF_SIFT_KP_PER_CTA (2 * EF_SIFT_WARPS)
-#define EF_SIFT_REC 913                 // odd: the second keypoint of a warp lands on the other bank parity
+#define EF_SIFT_REC 916                 // floats per record array (30x30 skewed needs 906)
+#define EF_SIFT_BLK (2 * EF_SIFT_REC)   // record block of one keypoint (16-byte multiple): magnitudes then fractions
 #define EF_SIFT_WIN 48                  // staged window edge (pixels); every sample of a size-31 patch lies in [k-22, k+22]
-#define EF_SIFT_WIN_WORDS 13            // 48 pixels + up to 3 alignment bytes
-#define EF_SIFT_WIN_PITCH (4 * EF_SIFT_WIN_WORDS)
+#define EF_SIFT_WIN_PITCH 80            // bytes: 64 loaded (48 pixels + up to 15 alignment bytes), 20-word pitch spreads the banks
 
 struct EfSiftWarpSmem {                 // per warp = 2 keypoints
     float hist[9 * 32];                 // [bin 0..8][lane]
-    float magp[2][EF_SIFT_REC];         // magnitude, sign bit = bin bit 2; phase 1 aliases the staging window here
-    float ofp[2][EF_SIFT_REC];          // orientation fraction, bits 31:30 = bin bits 1:0
+    // per keypoint k: magnitude[i] (sign bit = bin bit 2) at rec[k][k + i], fraction[i] (bits 31:30 = bin bits 1:0) at
+    // rec[k][REC + k + i]: the "+ k" puts the second keypoint on the other bank parity.  Phase 1 aliases the staging window here.
+    __align__(16) float rec[2][EF_SIFT_BLK + 4];
     float desc[2][128];
     uint8_t patch[2][32 * 32];
 };
-static_assert(EF_SIFT_WIN * EF_SIFT_WIN_WORDS <= EF_SIFT_REC, "staging window must fit the record array it aliases");
+static_assert(EF_SIFT_WIN * EF_SIFT_WIN_PITCH <= EF_SIFT_BLK * 4, "staging window must fit the record block it aliases");
+static_assert((EF_SIFT_BLK + 4) % 4 == 0, "record blocks must stay 16-byte aligned");
 
 // normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
 __device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
@@ -60,7 +62,7 @@ __device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
 }
 
 // All 32 lanes call this; lanes 0-15 work on keypoint slot 0 of the warp, lanes 16-31 on slot 1.
-// STAGED: integer keypoint, size 31, scale 1 (detectAndCompute path): window staging; image base and pitch 4-byte aligned.
+// STAGED: integer keypoint, size 31, scale 1 (detectAndCompute path): window staging; image base and pitch 16-byte aligned.
 template <bool STAGED>
 __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
                                                 float kx, float ky, float size, float angle, float croppingScale,
@@ -81,22 +83,21 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const uint8_t* base = img;
         int bpitch = pitch, ox = 0, oy = 0;
         if (STAGED) {
+            // 48 rows x 64 bytes (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy
             const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - EF_SIFT_WIN / 2;
-            const int gx0 = wx0 & ~3;
-            unsigned* win = reinterpret_cast<unsigned*>(sm.magp[k]);
-            if (hl < EF_SIFT_WIN_WORDS) {
-                const int gxw = gx0 + 4 * hl;
-                const bool colok = gxw >= 0 && gxw + 3 < pitch;
-#pragma unroll 8
-                for (int row = 0; row < EF_SIFT_WIN; row++) {
-                    const int gy = wy0 + row;
-                    unsigned v = 0;
-                    if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gxw));
-                    win[row * EF_SIFT_WIN_WORDS + hl] = v;
-                }
+            const int gx0 = wx0 & ~15;
+            uint8_t* win = reinterpret_cast<uint8_t*>(sm.rec[k]);
+            const int gxc = gx0 + 16 * (hl & 3);
+            const bool colok = gxc >= 0 && gxc + 15 < pitch;
+#pragma unroll
+            for (int it = 0; it < EF_SIFT_WIN / 4; it++) {
+                const int row = 4 * it + (hl >> 2), gy = wy0 + row;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
+                *reinterpret_cast<uint4*>(win + row * EF_SIFT_WIN_PITCH + 16 * (hl & 3)) = v;
             }
             __syncwarp();
-            base = reinterpret_cast<const uint8_t*>(win); bpitch = EF_SIFT_WIN_PITCH; ox = gx0; oy = wy0;
+            base = win; bpitch = EF_SIFT_WIN_PITCH; ox = gx0; oy = wy0;
         }
         const float cx0 = M00 * (float)hl, cx1 = M00 * (float)(hl + 16);
         const float cy0 = M10 * (float)hl, cy1 = M10 * (float)(hl + 16);
@@ -125,9 +126,10 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     __syncwarp();
     // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu)
     {
-        float* magp = sm.magp[k];
-        float* ofp = sm.ofp[k];
+        float* magp = sm.rec[k] + k;
+        float* ofp = sm.rec[k] + EF_SIFT_REC + k;
         int x = hl, y = 0;
+#pragma unroll 4
         for (int i = hl; i < 900; i += 16) {
             const uint8_t* c = patch + (y + 1) * 32 + x + 1;
             const int dxi = (int)c[1] - (int)c[-1];
@@ -145,8 +147,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     // ---- trilinear histogram (hash_sift.cpp:233-290); cell (rb, cb) in 1..4
     {
         const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
-        const float* mp = sm.magp[k];
-        const unsigned* op = reinterpret_cast<const unsigned*>(sm.ofp[k]);
+        const float* mp = sm.rec[k] + k;
+        const unsigned* op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
         float* hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
 #pragma unroll
