@@ -118,6 +118,11 @@ struct ef_handle {
     uint8_t* d_out_desc = nullptr; size_t out_desc_stride = 0;
     int* d_out_counts = nullptr;
     int* h_counts_pinned = nullptr;
+    // host API pipeline: upload / download streams and per-chunk events (upload of chunk c+1 and download of chunk c-1
+    // overlap the kernels of chunk c)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_cnt;
+    int host_chunk = 2;
 
     // optional per-stage timing (bench.py): events recorded between the stages
     bool timing = false;
@@ -154,6 +159,11 @@ void free_all(ef_handle* h)
     cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
     cudaFree(h->d_in); cudaFree(h->d_out_kpts); cudaFree(h->d_out_desc); cudaFree(h->d_out_counts);
     if (h->h_counts_pinned) cudaFreeHost(h->h_counts_pinned);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_cnt) cudaEventDestroy(e);
+    h->ev_in.clear(); h->ev_cnt.clear(); h->s_in = h->s_out = nullptr; h->h_counts_pinned = nullptr;
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     h->ev_pool.clear(); h->ev_stage.clear(); h->ev_used = 0;
 }
@@ -361,6 +371,13 @@ int allocate(ef_handle* h)
     EF_CUDA(h, alloc((void**)&h->d_out_desc, h->out_desc_stride * p.max_batch));
     EF_CUDA(h, alloc((void**)&h->d_out_counts, sizeof(int) * p.max_batch));
     EF_CUDA(h, cudaMallocHost((void**)&h->h_counts_pinned, sizeof(int) * (p.max_batch + EF_MAX_LEVELS * 4)));
+    EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    h->ev_in.resize(p.max_batch); h->ev_cnt.resize(p.max_batch);
+    for (int i = 0; i < p.max_batch; i++) {
+        EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_cnt[i], cudaEventDisableTiming));
+    }
     h->total_bytes = total;
     return EF_OK;
 }
@@ -662,26 +679,44 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t s = (cudaStream_t)stream;
     const int nf = h->prm.nfeatures, db = desc_bytes_of(h->prm.desc_type);
-    // upload (getInputMat, cuda_efficient_features.cpp:71-77)
-    for (int f = 0; f < nframes; f++)
-        EF_CUDA(h, cudaMemcpy2DAsync(h->d_in + f * h->in_stride, h->in_pitch, h_imgs + f * img_stride, pitch, width, height, cudaMemcpyHostToDevice, s));
-    int rc = ef_detect_and_compute_batch_async(h, nframes, h->d_in, h->in_stride, h->in_pitch, width, height,
-                                               h->d_out_kpts, h->out_kpts_stride, h->out_kpts_pitch,
-                                               h_desc ? h->d_out_desc : nullptr, h->out_desc_stride, (size_t)db, h->d_out_counts, s);
-    if (rc != EF_OK) return rc;
-    // the single host synchronisation needed to size the outputs (the reference needs 16 per frame)
-    EF_CUDA(h, cudaMemcpyAsync(h->h_counts_pinned, h->d_out_counts, sizeof(int) * nframes, cudaMemcpyDeviceToHost, s));
-    EF_CUDA(h, cudaStreamSynchronize(s));
-    for (int f = 0; f < nframes; f++) {
-        const int n = h->h_counts_pinned[f];
-        h_counts[f] = n;
-        if (n <= 0) continue;
-        // download (cuda_efficient_features.cpp:316-320); host layout: 5 x nfeatures floats, nfeatures x db bytes per frame
-        EF_CUDA(h, cudaMemcpy2DAsync(h_kpts5 + (size_t)f * EF_ROWS_COUNT * nf, (size_t)nf * 4, (uint8_t*)h->d_out_kpts + f * h->out_kpts_stride,
-                                     h->out_kpts_pitch, (size_t)n * 4, EF_ROWS_COUNT, cudaMemcpyDeviceToHost, s));
-        if (h_desc)
-            EF_CUDA(h, cudaMemcpyAsync(h_desc + (size_t)f * nf * db, h->d_out_desc + f * h->out_desc_stride, (size_t)n * db, cudaMemcpyDeviceToHost, s));
+    // Chunked pipeline over three streams: the upload of chunk c+1 (getInputMat, cuda_efficient_features.cpp:71-77) and the
+    // download of chunk c-1 (:316-320) overlap the kernels of chunk c.  Chunks reuse workspace slots [0, chunk): their
+    // kernels are serialised on the caller's stream; outputs land in per-frame staging buffers.
+    const int chunk = std::max(1, std::min(h->host_chunk, nframes));
+    const int nchunks = ef_div_up(nframes, chunk);
+    EF_CUDA(h, cudaEventRecord(h->ev_in[0], s));          // order the uploads after earlier work on the caller's stream
+    EF_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0));
+    for (int c = 0; c < nchunks; c++) {
+        for (int f = c * chunk; f < std::min(nframes, (c + 1) * chunk); f++)
+            EF_CUDA(h, cudaMemcpy2DAsync(h->d_in + f * h->in_stride, h->in_pitch, h_imgs + f * img_stride, pitch, width, height, cudaMemcpyHostToDevice, h->s_in));
+        EF_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
     }
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk, n = std::min(nframes, f0 + chunk) - f0;
+        EF_CUDA(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
+        int rc = ef_detect_and_compute_batch_async(h, n, h->d_in + f0 * h->in_stride, h->in_stride, h->in_pitch, width, height,
+                                                   (float*)((uint8_t*)h->d_out_kpts + f0 * h->out_kpts_stride), h->out_kpts_stride, h->out_kpts_pitch,
+                                                   h_desc ? h->d_out_desc + f0 * h->out_desc_stride : nullptr, h->out_desc_stride, (size_t)db,
+                                                   h->d_out_counts + f0, s);
+        if (rc != EF_OK) { cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(s); return rc; }
+        EF_CUDA(h, cudaMemcpyAsync(h->h_counts_pinned + f0, h->d_out_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+        EF_CUDA(h, cudaEventRecord(h->ev_cnt[c], s));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        // one host wait per chunk to size the outputs (the reference blocks 16 times per frame); later chunks keep running
+        EF_CUDA(h, cudaEventSynchronize(h->ev_cnt[c]));
+        for (int f = c * chunk; f < std::min(nframes, (c + 1) * chunk); f++) {
+            const int n = h->h_counts_pinned[f];
+            h_counts[f] = n;
+            if (n <= 0) continue;
+            // host layout: 5 x nfeatures floats, nfeatures x db bytes per frame
+            EF_CUDA(h, cudaMemcpy2DAsync(h_kpts5 + (size_t)f * EF_ROWS_COUNT * nf, (size_t)nf * 4, (uint8_t*)h->d_out_kpts + f * h->out_kpts_stride,
+                                         h->out_kpts_pitch, (size_t)n * 4, EF_ROWS_COUNT, cudaMemcpyDeviceToHost, h->s_out));
+            if (h_desc)
+                EF_CUDA(h, cudaMemcpyAsync(h_desc + (size_t)f * nf * db, h->d_out_desc + f * h->out_desc_stride, (size_t)n * db, cudaMemcpyDeviceToHost, h->s_out));
+        }
+    }
+    EF_CUDA(h, cudaStreamSynchronize(h->s_out));
     EF_CUDA(h, cudaStreamSynchronize(s));
     return EF_OK;
 }

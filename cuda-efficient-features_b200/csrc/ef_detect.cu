@@ -62,12 +62,114 @@ __global__ void __launch_bounds__(256) ef_resize_kernel(const __grid_constant__ 
     *reinterpret_cast<unsigned*>(dst + x0) = packed; // img_pitch is a multiple of 128
 }
 
+// Tiled form: one CTA = 128 x 32 output pixels.  The source window (about 156 x 41 pixels for a factor 1.2) is staged in shared
+// memory ONCE, read with aligned 32-bit words and converted to fp32 there (one conversion per source pixel instead of four per
+// output pixel); a warp then owns 4 output rows, a lane 4 adjacent output columns whose source offsets and horizontal weights
+// are computed once.  Same arithmetic as ef_resize_kernel, bit for bit.
+#define RS_TW 128
+#define RS_TH 32
+__global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_constant__ EfPipe p, const int level, const int RWp, const int RH)
+{
+    extern __shared__ __align__(16) float s_src[]; // RH rows x RWp floats
+
+    const EfLevel& L = p.lv[level];
+    const EfLevel& S = p.lv[level - 1];
+    const int frame = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * RS_TW, Y0 = blockIdx.y * RS_TH;
+
+    int spitch;
+    const uint8_t* __restrict__ src = ef_level_image(p, frame, level - 1, spitch);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (unsigned)spitch) & 3u) == 0;
+
+    // source window of the tile
+    const int xlast = min(X0 + RS_TW, L.w) - 1, ylast = min(Y0 + RS_TH, L.h) - 1;
+    const int sx0 = __float2int_rd((float)X0 * L.rx) & ~3;
+    const int sy0 = __float2int_rd((float)Y0 * L.ry);
+    const int sx1 = min(__float2int_rd((float)xlast * L.rx) + 1, S.w - 1);
+    const int sy1 = min(__float2int_rd((float)ylast * L.ry) + 1, S.h - 1);
+    const int nwords = min((sx1 - sx0) / 4 + 1, RWp / 4), nrows = min(sy1 - sy0 + 1, RH);
+    for (int row = warp; row < nrows; row += 8) {
+        const uint8_t* rp = src + (size_t)(sy0 + row) * spitch;
+        for (int wx = lane; wx < nwords; wx += 32) {
+            const int gx = sx0 + 4 * wx;
+            unsigned word;
+            if (aligned && gx + 3 < S.w) word = *reinterpret_cast<const unsigned*>(rp + gx);
+            else {
+                word = rp[gx];
+                if (gx + 1 < S.w) word |= (unsigned)rp[gx + 1] << 8;
+                if (gx + 2 < S.w) word |= (unsigned)rp[gx + 2] << 16;
+                if (gx + 3 < S.w) word |= (unsigned)rp[gx + 3] << 24;
+            }
+            float4 f;
+            f.x = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.f; // 0x4B0000bb = 2^23 + b, exact
+            f.y = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.f;
+            f.z = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.f;
+            f.w = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7543)) - 8388608.f;
+            *reinterpret_cast<float4*>(&s_src[row * RWp + 4 * wx]) = f;
+        }
+    }
+    __syncthreads();
+
+    // per-lane column geometry (4 adjacent output pixels)
+    const int x0 = X0 + 4 * lane;
+    if (x0 >= L.w) return;
+    int o1[4], o2[4];
+    float wx1[4], wx2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = min(x0 + j, L.w - 1);
+        const float sx = (float)x * L.rx;
+        const int x1 = __float2int_rd(sx);
+        const int x2 = x1 + 1;
+        o1[j] = x1 - sx0; o2[j] = min(x2, S.w - 1) - sx0;
+        wx1[j] = (float)x2 - sx; wx2[j] = sx - (float)x1;
+    }
+    uint8_t* dst = ef_ws(p, frame, L.img_off);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int y = Y0 + 4 * warp + r;
+        if (y >= L.h) break;
+        const float sy = (float)y * L.ry;
+        const int y1 = __float2int_rd(sy);
+        const int y2 = y1 + 1;
+        const float wy1 = (float)y2 - sy, wy2 = sy - (float)y1;
+        const float* ra = s_src + (y1 - sy0) * RWp;
+        const float* rb = s_src + (min(y2, S.h - 1) - sy0) * RWp;
+        unsigned packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float out = 0.f;
+            out = fmaf(ra[o1[j]], wx1[j] * wy1, out);
+            out = fmaf(ra[o2[j]], wx2[j] * wy1, out);
+            out = fmaf(rb[o1[j]], wx1[j] * wy2, out);
+            out = fmaf(rb[o2[j]], wx2[j] * wy2, out);
+            packed |= ef_sat_u8_rne(out) << (8 * j);
+        }
+        *reinterpret_cast<unsigned*>(dst + (size_t)y * L.img_pitch + x0) = packed; // img_pitch is a multiple of 128
+    }
+}
+
 void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
 {
+    static size_t configured = 0;
     for (int l = 1; l < p.nlevels; l++) {
-        const dim3 block(64, 4);
-        const dim3 grid(ef_div_up(p.lv[l].w, 256), ef_div_up(p.lv[l].h, 4), p.nframes);
-        ef_resize_kernel<<<grid, block, 0, s>>>(p, l);
+        // staged source window: ceil(tile * ratio) + slack for the floor/+1/alignment; falls back to the direct kernel if it cannot fit
+        const int RWp = (((int)ceilf(RS_TW * p.lv[l].rx) + 8) + 3) & ~3;
+        const int RH = (int)ceilf(RS_TH * p.lv[l].ry) + 3;
+        const size_t smem = (size_t)RWp * RH * sizeof(float);
+        if (smem <= 200 * 1024) {
+            if (smem > 48 * 1024 && smem > configured) {
+                cudaFuncSetAttribute(ef_resize_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured = smem;
+            }
+            const dim3 grid(ef_div_up(p.lv[l].w, RS_TW), ef_div_up(p.lv[l].h, RS_TH), p.nframes);
+            ef_resize_tiled_kernel<<<grid, 256, smem, s>>>(p, l, RWp, RH);
+        } else {
+            const dim3 block(64, 4);
+            const dim3 grid(ef_div_up(p.lv[l].w, 256), ef_div_up(p.lv[l].h, 4), p.nframes);
+            ef_resize_kernel<<<grid, block, 0, s>>>(p, l);
+        }
         EF_COUNT_LAUNCH(1);
     }
 }
@@ -115,8 +217,8 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
     __shared__ __align__(16) unsigned s_h1[SC_ROWS][SC_HW];
     __shared__ __align__(16) float2 s_grad[SC_GROWS][SC_ROWS];
     __shared__ __align__(16) float s_resp[EF_TILE][EF_TILE];
-    __shared__ unsigned short s_list[EF_TILE * EF_TILE];
-    __shared__ int s_n;
+    __shared__ unsigned short s_list[2][EF_TILE * EF_TILE / 2]; // corners with even / odd tile column
+    __shared__ int s_n[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
@@ -131,37 +233,40 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
     const bool aligned = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0;
 
     // ---- tile + halo -> fp16 pairs.  Pixels outside the image read as 0: no corner lies within 15 px of the border and
-    //      neither the ring (3) nor the Harris window (4) reaches them.
-    if (tid == 0) s_n = 0;
-    for (int i = tid; i < SC_ROWS * 10; i += 256) {
-        const int row = i / 10, wx = i - row * 10;
-        const int gy = y0 - SC_HALO + row, gx = x0 - SC_HALO + 4 * wx;
-        unsigned word = 0;
-        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.w) {
-            const uint8_t* rp = img + (size_t)gy * pitch + gx;
-            if (aligned && gx + 3 < L.w) word = *reinterpret_cast<const unsigned*>(rp);
-            else {
-                word = rp[0];
-                if (gx + 1 < L.w) word |= (unsigned)rp[1] << 8;
-                if (gx + 2 < L.w) word |= (unsigned)rp[2] << 16;
-                if (gx + 3 < L.w) word |= (unsigned)rp[3] << 24;
+    //      neither the ring (3) nor the Harris window (4) reaches them.  A warp takes 3 rows of 10 words per step; the
+    //      shifted copy s_h1 (pair j = pixels j+1, j+2) needs the first pixel of the next word: one shuffle.
+    if (tid < 2) s_n[tid] = 0;
+    {
+        const int rsub = lane / 10, wx = lane - rsub * 10;
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int row = 3 * (warp + 8 * it) + rsub;
+            const bool act = lane < 30 && row < SC_ROWS;
+            const int gy = y0 - SC_HALO + row, gx = x0 - SC_HALO + 4 * wx;
+            unsigned word = 0;
+            if (act && gy >= 0 && gy < L.h && gx >= 0 && gx < L.w) {
+                const uint8_t* rp = img + (size_t)gy * pitch + gx;
+                if (aligned && gx + 3 < L.w) word = *reinterpret_cast<const unsigned*>(rp);
+                else {
+                    word = rp[0];
+                    if (gx + 1 < L.w) word |= (unsigned)rp[1] << 8;
+                    if (gx + 2 < L.w) word |= (unsigned)rp[2] << 16;
+                    if (gx + 3 < L.w) word |= (unsigned)rp[3] << 24;
+                }
+            }
+            // bytes -> halves: 0x6400 | b is the half 1024 + b; subtracting 1024 is exact
+            const unsigned k1024 = 0x64006400u;
+            unsigned h01 = __byte_perm(word, 0x64646464u, 0x4140), h23 = __byte_perm(word, 0x64646464u, 0x4342);
+            const __half2 a = __hsub2(*reinterpret_cast<__half2*>(&h01), *reinterpret_cast<const __half2*>(&k1024));
+            const __half2 b = __hsub2(*reinterpret_cast<__half2*>(&h23), *reinterpret_cast<const __half2*>(&k1024));
+            const unsigned ua = *reinterpret_cast<const unsigned*>(&a), ub = *reinterpret_cast<const unsigned*>(&b);
+            const unsigned un = __shfl_down_sync(0xffffffffu, ua, 1); // pixels 4wx+4, 4wx+5 (garbage for wx = 9: pixel 40 is never used)
+            if (act) {
+                *reinterpret_cast<uint2*>(&s_h0[row][SC_PAD / 2 + 2 * wx]) = make_uint2(ua, ub);
+                *reinterpret_cast<uint2*>(&s_h1[row][SC_PAD / 2 + 2 * wx]) = make_uint2(__byte_perm(ua, ub, 0x5432), __byte_perm(ub, un, 0x5432));
+                if (wx == 0) s_h1[row][SC_PAD / 2 - 1] = ua << 16; // pair j = -2: (pixel -1: unused, pixel 0)
             }
         }
-        // bytes -> halves: 0x6400 | b is the half 1024 + b; subtracting 1024 is exact
-        const unsigned k1024 = 0x64006400u;
-        unsigned h01 = __byte_perm(word, 0x64646464u, 0x4140), h23 = __byte_perm(word, 0x64646464u, 0x4342);
-        __half2 a = __hsub2(*reinterpret_cast<__half2*>(&h01), *reinterpret_cast<const __half2*>(&k1024));
-        __half2 b = __hsub2(*reinterpret_cast<__half2*>(&h23), *reinterpret_cast<const __half2*>(&k1024));
-        uint2 o;
-        o.x = *reinterpret_cast<unsigned*>(&a); o.y = *reinterpret_cast<unsigned*>(&b);
-        *reinterpret_cast<uint2*>(&s_h0[row][SC_PAD / 2 + 2 * wx]) = o;
-    }
-    __syncthreads();
-    // shifted copy: pair j of s_h1 = (pixel j+1, pixel j+2), j = -2, 0, ..., 38
-    for (int i = tid; i < SC_ROWS * 21; i += 256) {
-        const int row = i / 21, jj = i - row * 21;      // pair index jj <-> j = 2*jj - 2 <-> word SC_PAD/2 + jj - 1
-        const unsigned A = s_h0[row][SC_PAD / 2 + jj - 1], B = s_h0[row][SC_PAD / 2 + jj];
-        s_h1[row][SC_PAD / 2 + jj - 1] = __byte_perm(A, B, 0x5432);
     }
     __syncthreads();
 
@@ -197,17 +302,17 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             const bool c1 = rowok && (arc >> 16) != 0 && gx + 1 >= EF_HALF_PATCH && gx + 1 < L.w - EF_HALF_PATCH;
             *reinterpret_cast<float2*>(&s_resp[py][px]) = make_float2(EF_NEG_INF, EF_NEG_INF);
             const unsigned bal0 = __ballot_sync(0xffffffffu, c0), bal1 = __ballot_sync(0xffffffffu, c1);
-            const int n0 = __popc(bal0), cnt = n0 + __popc(bal1);
             int base = 0;
-            if (lane == 0 && cnt) base = atomicAdd(&s_n, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < 2) { const int cnt = __popc(lane ? bal1 : bal0); if (cnt) base = atomicAdd(&s_n[lane], cnt); }
+            const int base0 = __shfl_sync(0xffffffffu, base, 0), base1 = __shfl_sync(0xffffffffu, base, 1);
             const unsigned lt = (1u << lane) - 1u;
-            if (c0) s_list[base + __popc(bal0 & lt)] = (unsigned short)((py << 5) | px);
-            if (c1) s_list[base + n0 + __popc(bal1 & lt)] = (unsigned short)((py << 5) | (px + 1));
+            if (c0) s_list[0][base0 + __popc(bal0 & lt)] = (unsigned short)((py << 5) | px);
+            if (c1) s_list[1][base1 + __popc(bal1 & lt)] = (unsigned short)((py << 5) | (px + 1));
         }
     }
     __syncthreads();
-    const int n = s_n;
+    const int n_even = s_n[0], n_odd = s_n[1];
+    const int n = n_even + n_odd;
 
     if (n > 0) {
         // ---- Sobel gradients of tile-local rows/columns 1..38 (cuda_efficient_features.cu:116-128), two pixels per thread:
@@ -235,21 +340,46 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             *reinterpret_cast<float4*>(&s_grad[row][2 * pr]) = g;
         }
         __syncthreads();
-        // ---- Harris, raster order over the 7x7 block with the reference's contraction
-        for (int i = tid; i < n; i += 256) {
-            const int pos = s_list[i];
+        // ---- Harris, raster order over the 7x7 block with the reference's contraction:
+        //      sxx = fmaf(gx,gx,sxx), sxy = fmaf(gx,gy,sxy), syy = fmaf(gy,gy,syy) per tap.  (sxx, syy) advance together in one
+        //      packed FFMA2 (fma.rn.f32x2, per-lane IEEE).  The window columns are cx+1 .. cx+7 of s_grad: for an odd cx they
+        //      start on a 16-byte boundary (3 x LDS.128 + LDS.64 per row), for an even cx one tap later -- the two parity lists
+        //      keep every warp on one of the two layouts.
+        const int npad_even = (n_even + 31) & ~31;       // odd-list work starts on a fresh warp
+        for (int i = tid; i < npad_even + n_odd; i += 256) {
+            const bool odd = i >= npad_even;
+            const int li = odd ? i - npad_even : i;
+            if (!odd && li >= n_even) continue;
+            const int pos = s_list[odd ? 1 : 0][li];
             const int cx = pos & 31, cy = pos >> 5;
-            float sxx = 0.f, sxy = 0.f, syy = 0.f;
+            unsigned long long acc = 0ull; // (sxx, syy)
+            float sxy = 0.f;
+#define EF_TAP(G) { const unsigned long long g_ = (G); float gx_, gy_; \
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(gx_), "=f"(gy_) : "l"(g_)); \
+                    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(g_)); \
+                    sxy = fmaf(gx_, gy_, sxy); }
+            if (odd) {
 #pragma unroll
-            for (int iy = 0; iy < 7; iy++) {
+                for (int iy = 0; iy < 7; iy++) {
+                    const float2* row = &s_grad[cy + iy][cx + 1];
+                    const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(row), q1 = *reinterpret_cast<const ulonglong2*>(row + 2),
+                                     q2 = *reinterpret_cast<const ulonglong2*>(row + 4);
+                    const unsigned long long q3 = *reinterpret_cast<const unsigned long long*>(row + 6);
+                    EF_TAP(q0.x) EF_TAP(q0.y) EF_TAP(q1.x) EF_TAP(q1.y) EF_TAP(q2.x) EF_TAP(q2.y) EF_TAP(q3)
+                }
+            } else {
 #pragma unroll
-                for (int ix = 0; ix < 7; ix++) {
-                    const float2 g = s_grad[cy + iy][cx + 1 + ix];
-                    sxx = fmaf(g.x, g.x, sxx);
-                    sxy = fmaf(g.x, g.y, sxy);
-                    syy = fmaf(g.y, g.y, syy);
+                for (int iy = 0; iy < 7; iy++) {
+                    const float2* row = &s_grad[cy + iy][cx + 1];
+                    const unsigned long long q0 = *reinterpret_cast<const unsigned long long*>(row);
+                    const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(row + 1), q2 = *reinterpret_cast<const ulonglong2*>(row + 3),
+                                     q3 = *reinterpret_cast<const ulonglong2*>(row + 5);
+                    EF_TAP(q0) EF_TAP(q1.x) EF_TAP(q1.y) EF_TAP(q2.x) EF_TAP(q2.y) EF_TAP(q3.x) EF_TAP(q3.y)
                 }
             }
+#undef EF_TAP
+            float sxx, syy;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sxx), "=f"(syy) : "l"(acc));
             const float p2 = sxy * sxy;
             const float det = fmaf(sxx, syy, -p2);
             const float tr = sxx + syy;
@@ -803,7 +933,7 @@ __device__ __forceinline__ float ef_byte_to_float(unsigned word, int i)
     return __uint_as_float(m) - 8388608.f;
 }
 
-__global__ void __launch_bounds__(256) ef_blur_kernel(const __grid_constant__ EfPipe p)
+__global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ unsigned s_in[BL_TH + 6][BL_IW];
     __shared__ __align__(16) float s_row[BL_TH + 6][BL_TW];
@@ -822,7 +952,10 @@ __global__ void __launch_bounds__(256) ef_blur_kernel(const __grid_constant__ Ef
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
     const bool fast = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0 && x0 >= 4 && x0 + BL_TW + 4 <= L.w;
 
-    for (int i = tid; i < (BL_TH + 6) * BL_IW; i += 256) {
+#pragma unroll
+    for (int it = 0; it < ((BL_TH + 6) * BL_IW + 255) / 256; it++) {
+        const int i = tid + 256 * it;
+        if (i >= (BL_TH + 6) * BL_IW) break;
         const int ly = i / BL_IW, wx = i - ly * BL_IW;
         const int gy = ef_reflect101(min(y0 - 3 + ly, L.h + 2), L.h);
         const uint8_t* rp = img + (size_t)gy * pitch;

@@ -129,7 +129,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         float* magp = sm.rec[k] + k;
         float* ofp = sm.rec[k] + EF_SIFT_REC + k;
         int x = hl, y = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = hl; i < 900; i += 16) {
             const uint8_t* c = patch + (y + 1) * 32 + x + 1;
             const int dxi = (int)c[1] - (int)c[-1];
@@ -151,6 +151,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const unsigned* op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
         float* hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
+        // Out-of-patch visits (rows/columns outside 0..29 for the border cells) are not branched around: they read record 0 and
+        // add +0.0f, which leaves every (non-negative) accumulator unchanged -- the warp executes the iteration anyway.
 #pragma unroll
         for (int rseg = 0; rseg < 2; rseg++) {
             for (int iy = 0; iy < 8; iy++) {
@@ -163,23 +165,23 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
 #pragma unroll
                     for (int ix = 0; ix < 8; ix++) {
                         const int xo = 8 * cseg + ix;
-                        if (rowok && (unsigned)(xb + xo) < 30u) {
-                            const float mg = mp[rowidx + xo];
-                            const unsigned ob = op[rowidx + xo];
-                            const float mag = fabsf(mg);
-                            const unsigned oi = (ob >> 30) | ((__float_as_uint(mg) >> 31) << 2);
-                            const float of = __uint_as_float(ob & 0x3fffffffu);
-                            // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
-                            const float v1 = rf * mag;
-                            const float vr = rseg == 0 ? v1 : mag - v1;
-                            const float c1 = (0.125f * (float)ix) * vr;
-                            const float vc = cseg == 0 ? c1 : vr - c1;
-                            const float vo1 = of * vc, vo0 = vc - vo1;
-                            float* h0 = hc + oi * 32;
-                            const float a0 = h0[0], a1 = h0[32];
-                            h0[0] = a0 + vo0;
-                            h0[32] = a1 + vo1;
-                        }
+                        const bool ok = rowok && (unsigned)(xb + xo) < 30u;
+                        const int idx = ok ? rowidx + xo : 0;
+                        const float mg = mp[idx];
+                        const unsigned ob = op[idx];
+                        const float mag = ok ? fabsf(mg) : 0.f;
+                        const unsigned oi = (ob >> 30) | ((__float_as_uint(mg) >> 31) << 2);
+                        const float of = __uint_as_float(ob & 0x3fffffffu);
+                        // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
+                        const float v1 = rf * mag;
+                        const float vr = rseg == 0 ? v1 : mag - v1;
+                        const float c1 = (0.125f * (float)ix) * vr;
+                        const float vc = cseg == 0 ? c1 : vr - c1;
+                        const float vo1 = of * vc, vo0 = vc - vo1;
+                        float* h0 = hc + oi * 32;
+                        const float a0 = h0[0], a1 = h0[32];
+                        h0[0] = a0 + vo0;
+                        h0[32] = a1 + vo1;
                     }
                 }
             }
