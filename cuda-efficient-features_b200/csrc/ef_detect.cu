@@ -62,15 +62,40 @@ __global__ void __launch_bounds__(256) ef_resize_kernel(const __grid_constant__ 
     *reinterpret_cast<unsigned*>(dst + x0) = packed; // img_pitch is a multiple of 128
 }
 
-// Tiled form: one CTA = 128 x 32 output pixels.  The source window (about 156 x 41 pixels for a factor 1.2) is staged in shared
-// memory ONCE, read with aligned 32-bit words and converted to fp32 there (one conversion per source pixel instead of four per
-// output pixel); a warp then owns 4 output rows, a lane 4 adjacent output columns whose source offsets and horizontal weights
-// are computed once.  Same arithmetic as ef_resize_kernel, bit for bit.
+// Tiled form (resize ratios <= 1.21 x 1.25, i.e. the usual 1.2 pyramid): one CTA = 128 x 32 output pixels.  The source window
+// (<= 160 x 43 pixels) is staged in shared memory ONCE, read with aligned 32-bit words and converted to fp32 there (one
+// conversion per source pixel instead of four per output pixel).  The column one past the right edge and the row one past the
+// bottom edge are staged as copies of the last column / row, so the x2r / y2r clamps of the direct kernel vanish: the four
+// taps of a pixel are s[o], s[o+1], s[o+RWP], s[o+RWP+1] -- one address per pixel, immediate offsets for the rest.
+// A warp owns 4 output rows, a lane 4 adjacent output columns whose source offsets and horizontal weights are computed once;
+// two pixels advance together in packed fp32 (FMUL2 / FFMA2: mul.rn.f32x2, fma.rn.f32x2 -- per-lane IEEE, so the arithmetic
+// is that of ef_resize_kernel bit for bit).
 #define RS_TW 128
 #define RS_TH 32
-__global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_constant__ EfPipe p, const int level, const int RWp, const int RH)
+#define RS_RWP 160
+#define RS_RH 43
+__device__ __forceinline__ unsigned long long ef_pack2(float lo, float hi)
 {
-    extern __shared__ __align__(16) float s_src[]; // RH rows x RWp floats
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ef_mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ef_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_constant__ EfPipe p, const int level)
+{
+    __shared__ __align__(16) float s_src[RS_RH * RS_RWP];
 
     const EfLevel& L = p.lv[level];
     const EfLevel& S = p.lv[level - 1];
@@ -82,49 +107,50 @@ __global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_const
     const uint8_t* __restrict__ src = ef_level_image(p, frame, level - 1, spitch);
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (unsigned)spitch) & 3u) == 0;
 
-    // source window of the tile
+    // source window of the tile: columns sx0 .. x1(last)+1, rows sy0 .. y1(last)+1 (the +1 may be one past the edge: clamped copy)
     const int xlast = min(X0 + RS_TW, L.w) - 1, ylast = min(Y0 + RS_TH, L.h) - 1;
     const int sx0 = __float2int_rd((float)X0 * L.rx) & ~3;
     const int sy0 = __float2int_rd((float)Y0 * L.ry);
-    const int sx1 = min(__float2int_rd((float)xlast * L.rx) + 1, S.w - 1);
-    const int sy1 = min(__float2int_rd((float)ylast * L.ry) + 1, S.h - 1);
-    const int nwords = min((sx1 - sx0) / 4 + 1, RWp / 4), nrows = min(sy1 - sy0 + 1, RH);
-    for (int row = warp; row < nrows; row += 8) {
-        const uint8_t* rp = src + (size_t)(sy0 + row) * spitch;
-        for (int wx = lane; wx < nwords; wx += 32) {
-            const int gx = sx0 + 4 * wx;
-            unsigned word;
-            if (aligned && gx + 3 < S.w) word = *reinterpret_cast<const unsigned*>(rp + gx);
-            else {
-                word = rp[gx];
-                if (gx + 1 < S.w) word |= (unsigned)rp[gx + 1] << 8;
-                if (gx + 2 < S.w) word |= (unsigned)rp[gx + 2] << 16;
-                if (gx + 3 < S.w) word |= (unsigned)rp[gx + 3] << 24;
-            }
-            float4 f;
-            f.x = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.f; // 0x4B0000bb = 2^23 + b, exact
-            f.y = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.f;
-            f.z = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.f;
-            f.w = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7543)) - 8388608.f;
-            *reinterpret_cast<float4*>(&s_src[row * RWp + 4 * wx]) = f;
+    const int nwords = min((__float2int_rd((float)xlast * L.rx) + 1 - sx0) / 4 + 1, RS_RWP / 4);
+    const int nrows = min(__float2int_rd((float)ylast * L.ry) + 1 - sy0 + 1, RS_RH);
+    const unsigned inv = 0xffffffffu / (unsigned)nwords + 1u; // i / nwords == umulhi(i, inv) for the small i used here (nwords >= 2)
+#pragma unroll 2
+    for (int i = tid; i < nrows * nwords; i += 256) {
+        const int row = nwords == 1 ? i : (int)__umulhi((unsigned)i, inv), wx = i - row * nwords;
+        const uint8_t* rp = src + (size_t)min(sy0 + row, S.h - 1) * spitch;
+        const int gx = sx0 + 4 * wx;
+        unsigned word;
+        if (aligned && gx + 3 < S.w) word = *reinterpret_cast<const unsigned*>(rp + gx);
+        else {
+            word = rp[min(gx, S.w - 1)];
+            word |= (unsigned)rp[min(gx + 1, S.w - 1)] << 8;
+            word |= (unsigned)rp[min(gx + 2, S.w - 1)] << 16;
+            word |= (unsigned)rp[min(gx + 3, S.w - 1)] << 24;
         }
+        float4 f;
+        f.x = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.f; // 0x4B0000bb = 2^23 + b, exact
+        f.y = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.f;
+        f.z = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.f;
+        f.w = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7543)) - 8388608.f;
+        *reinterpret_cast<float4*>(&s_src[row * RS_RWP + 4 * wx]) = f;
     }
     __syncthreads();
 
     // per-lane column geometry (4 adjacent output pixels)
     const int x0 = X0 + 4 * lane;
     if (x0 >= L.w) return;
-    int o1[4], o2[4];
+    int o[4];
     float wx1[4], wx2[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int x = min(x0 + j, L.w - 1);
         const float sx = (float)x * L.rx;
         const int x1 = __float2int_rd(sx);
-        const int x2 = x1 + 1;
-        o1[j] = x1 - sx0; o2[j] = min(x2, S.w - 1) - sx0;
-        wx1[j] = (float)x2 - sx; wx2[j] = sx - (float)x1;
+        o[j] = min(x1 - sx0, RS_RWP - 2);
+        wx1[j] = (float)(x1 + 1) - sx; wx2[j] = sx - (float)x1;
     }
+    const unsigned long long wx1a = ef_pack2(wx1[0], wx1[1]), wx1b = ef_pack2(wx1[2], wx1[3]);
+    const unsigned long long wx2a = ef_pack2(wx2[0], wx2[1]), wx2b = ef_pack2(wx2[2], wx2[3]);
     uint8_t* dst = ef_ws(p, frame, L.img_off);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -132,39 +158,33 @@ __global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_const
         if (y >= L.h) break;
         const float sy = (float)y * L.ry;
         const int y1 = __float2int_rd(sy);
-        const int y2 = y1 + 1;
-        const float wy1 = (float)y2 - sy, wy2 = sy - (float)y1;
-        const float* ra = s_src + (y1 - sy0) * RWp;
-        const float* rb = s_src + (min(y2, S.h - 1) - sy0) * RWp;
-        unsigned packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float out = 0.f;
-            out = fmaf(ra[o1[j]], wx1[j] * wy1, out);
-            out = fmaf(ra[o2[j]], wx2[j] * wy1, out);
-            out = fmaf(rb[o1[j]], wx1[j] * wy2, out);
-            out = fmaf(rb[o2[j]], wx2[j] * wy2, out);
-            packed |= ef_sat_u8_rne(out) << (8 * j);
-        }
+        const float wy1 = (float)(y1 + 1) - sy, wy2 = sy - (float)y1;
+        const float* ra = s_src + min(y1 - sy0, RS_RH - 2) * RS_RWP;
+        const unsigned long long wy1p = ef_pack2(wy1, wy1), wy2p = ef_pack2(wy2, wy2);
+        const float* q0 = ra + o[0]; const float* q1 = ra + o[1]; const float* q2 = ra + o[2]; const float* q3 = ra + o[3];
+        // pixels (0,1) and (2,3) advance together; tap order = ef_resize_kernel: (y1,x1) (y1,x2) (y2,x1) (y2,x2)
+        unsigned long long a = ef_mul2(ef_pack2(q0[0], q1[0]), ef_mul2(wx1a, wy1p));
+        unsigned long long b = ef_mul2(ef_pack2(q2[0], q3[0]), ef_mul2(wx1b, wy1p));
+        a = ef_fma2(ef_pack2(q0[1], q1[1]), ef_mul2(wx2a, wy1p), a);
+        b = ef_fma2(ef_pack2(q2[1], q3[1]), ef_mul2(wx2b, wy1p), b);
+        a = ef_fma2(ef_pack2(q0[RS_RWP], q1[RS_RWP]), ef_mul2(wx1a, wy2p), a);
+        b = ef_fma2(ef_pack2(q2[RS_RWP], q3[RS_RWP]), ef_mul2(wx1b, wy2p), b);
+        a = ef_fma2(ef_pack2(q0[RS_RWP + 1], q1[RS_RWP + 1]), ef_mul2(wx2a, wy2p), a);
+        b = ef_fma2(ef_pack2(q2[RS_RWP + 1], q3[RS_RWP + 1]), ef_mul2(wx2b, wy2p), b);
+        float o0, o1, o2, o3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(a));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o2), "=f"(o3) : "l"(b));
+        const unsigned packed = ef_sat_u8_rne(o0) | (ef_sat_u8_rne(o1) << 8) | (ef_sat_u8_rne(o2) << 16) | (ef_sat_u8_rne(o3) << 24);
         *reinterpret_cast<unsigned*>(dst + (size_t)y * L.img_pitch + x0) = packed; // img_pitch is a multiple of 128
     }
 }
 
 void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
 {
-    static size_t configured = 0;
     for (int l = 1; l < p.nlevels; l++) {
-        // staged source window: ceil(tile * ratio) + slack for the floor/+1/alignment; falls back to the direct kernel if it cannot fit
-        const int RWp = (((int)ceilf(RS_TW * p.lv[l].rx) + 8) + 3) & ~3;
-        const int RH = (int)ceilf(RS_TH * p.lv[l].ry) + 3;
-        const size_t smem = (size_t)RWp * RH * sizeof(float);
-        if (smem <= 200 * 1024) {
-            if (smem > 48 * 1024 && smem > configured) {
-                cudaFuncSetAttribute(ef_resize_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                configured = smem;
-            }
+        if (p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.25f) {
             const dim3 grid(ef_div_up(p.lv[l].w, RS_TW), ef_div_up(p.lv[l].h, RS_TH), p.nframes);
-            ef_resize_tiled_kernel<<<grid, 256, smem, s>>>(p, l, RWp, RH);
+            ef_resize_tiled_kernel<<<grid, 256, 0, s>>>(p, l);
         } else {
             const dim3 block(64, 4);
             const dim3 grid(ef_div_up(p.lv[l].w, 256), ef_div_up(p.lv[l].h, 4), p.nframes);

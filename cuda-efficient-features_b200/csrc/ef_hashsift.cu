@@ -101,6 +101,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         }
         const float cx0 = M00 * (float)hl, cx1 = M00 * (float)(hl + 16);
         const float cy0 = M10 * (float)hl, cy1 = M10 * (float)(hl + 16);
+#pragma unroll 4
         for (int y = 0; y < 32; y++) {
             const float ru = M01 * (float)y, rv = M11 * (float)y;
 #pragma unroll
