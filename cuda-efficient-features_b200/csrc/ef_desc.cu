@@ -146,14 +146,20 @@ __device__ __forceinline__ EfBadAffine ef_bad_affine(float kx, float ky, float s
     return a;
 }
 
-// integral accessors: I(y, x) with x in [0,w], y in [0,h]
-struct EfGlobalIntegral {
+// integral accessors.  box(y0, x0, y1, x1) = sum of the pixels in rows [y0, y1) x columns [x0, x1)
+struct EfGlobalIntegral { // (h+1) x (w+1) uint32 integral image of the whole frame (wrapping arithmetic, exact differences)
     const unsigned* I; int iw;
     __device__ __forceinline__ unsigned at(int y, int x) const { return __ldg(I + (size_t)y * iw + x); }
+    __device__ __forceinline__ unsigned box(int y0, int x0, int y1, int x1) const { return at(y0, x0) + at(y1, x1) - at(y0, x1) - at(y1, x0); }
 };
-struct EfWindowIntegral { // local integral of the (2*HALF) x (2*HALF) pixel window around an integer keypoint
-    const unsigned* W; int wx0, wy0, pitch;
-    __device__ __forceinline__ unsigned at(int y, int x) const { return W[(y - wy0) * pitch + (x - wx0)]; }
+// 16-bit modular integral of the 48-row window around a keypoint (ef_bad_pipe_kernel): P[r][a] (halfword r*PITCH + a + 1) =
+// sum over window rows < r of the bytes [0, a) of the 64-byte aligned row + a per-row constant that cancels in every box.
+// Exact for boxes whose true sum is < 2^16, i.e. radius <= 7 (15 x 15 x 255 = 57375): the detectAndCompute path (size 31, scale 1).
+#define EF_BW_PITCH 66 // halfwords per row: 65 entries + 1 so that entry pairs are word aligned; 33 words (odd) spreads the banks
+struct EfWindowIntegral16 {
+    const unsigned short* P; int gx0, wy0;
+    __device__ __forceinline__ unsigned at(int y, int x) const { return P[(y - wy0) * EF_BW_PITCH + (x - gx0) + 1]; }
+    __device__ __forceinline__ unsigned box(int y0, int x0, int y1, int x1) const { return (at(y0, x0) + at(y1, x1) - at(y0, x1) - at(y1, x0)) & 0xffffu; }
 };
 
 template <class Integral>
@@ -169,8 +175,7 @@ __device__ __forceinline__ bool ef_bad_bit(const Integral& I, const EfBadAffine&
     if (!a.border) {
         // bad.cpp:371-393: integer box sums, threshold scaled by the box area
         const int side = 1 + (r << 1);
-        const unsigned acc = I.at(y1 - r, x1 - r) + I.at(y1 + r + 1, x1 + r + 1) - I.at(y1 - r, x1 + r + 1) - I.at(y1 + r + 1, x1 - r)
-                           - I.at(y2 - r, x2 - r) - I.at(y2 + r + 1, x2 + r + 1) + I.at(y2 - r, x2 + r + 1) + I.at(y2 + r + 1, x2 - r);
+        const unsigned acc = I.box(y1 - r, x1 - r, y1 + r + 1, x1 + r + 1) - I.box(y2 - r, x2 - r, y2 + r + 1, x2 + r + 1);
         return (float)(int)acc <= (thr * (float)(side * side));
     }
     // bad.cpp:166-251: clamped boxes, float means.  frameWidth/Height = integral dims (w+1, h+1)
@@ -183,9 +188,9 @@ __device__ __forceinline__ bool ef_bad_bit(const Integral& I, const EfBadAffine&
     int by1i = y2 - r; if (by1i < 0) by1i = 0; else if (by1i >= fh - 1) by1i = fh - 2;
     int bx2i = x2 + r + 1; if (bx2i <= 0) bx2i = 1; else if (bx2i >= fw) bx2i = fw - 1;
     int by2i = y2 + r + 1; if (by2i <= 0) by2i = 1; else if (by2i >= fh) by2i = fh - 1;
-    const float sum1 = (float)(int)(I.at(ay1, ax1) + I.at(ay2, ax2) - I.at(ay1, ax2) - I.at(ay2, ax1));
+    const float sum1 = (float)(int)I.box(ay1, ax1, ay2, ax2);
     const float avg1 = sum1 / (float)((ay2 - ay1) * (ax2 - ax1));
-    const float sum2 = (float)(int)(I.at(by1i, bx1i) + I.at(by2i, bx2i) - I.at(by1i, bx2i) - I.at(by2i, bx1i));
+    const float sum2 = (float)(int)I.box(by1i, bx1i, by2i, bx2i);
     const float avg2 = sum2 / (float)((by2i - by1i) * (bx2i - bx1i));
     return (avg1 - avg2) <= thr;
 }
@@ -224,15 +229,19 @@ void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const Ef
 
 // ---- detectAndCompute path: keypoints from the per-level selected lists on the blurred level,
 //      size 31, scale 1 (cuda_efficient_features.cpp:48-69,306).  Every box corner then lies in
-//      [k-22, k+23] (exhaustive over both tables and all angles), so a 48x48-pixel window and its
-//      49x49 local integral in shared memory replace the reference's full-frame integral image.
+//      [k-22, k+23] (exhaustive over both tables and all angles), so the 48 window rows k-24 .. k+23, read as 64-byte
+//      aligned row segments (four 16-byte loads per row), and a 16-bit modular integral of them in shared memory
+//      (6.5 KB per keypoint) replace the reference's full-frame integral image (-4P writes, -4P reads per level).
+//        1. load: lane = (row mod 8, 16-byte chunk); row prefix in registers: 16 byte adds + a 4-lane shuffle scan
+//        2. column prefix in shared memory, two columns (one 32-bit word) per lane, halves added independently
+//        3. lane = box pair: 8 halfword lookups per pair, ballot + brev packs 32 descriptor bits
 #define EF_BW_HALF 24
-#define EF_BW_PIX (2 * EF_BW_HALF)      // 48 pixels
-#define EF_BW_INT (EF_BW_PIX + 1)       // 49 integral entries per side (odd pitch: conflict-free columns)
+#define EF_BW_ROWS (2 * EF_BW_HALF)     // 48 window rows
+#define EF_BW_WORDS (EF_BW_PITCH / 2)   // 33
 
 __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const __grid_constant__ EfPipe p, const EfBadTables t)
 {
-    extern __shared__ unsigned s_win_all[];
+    extern __shared__ __align__(16) unsigned s_win_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int frame = blockIdx.y;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
@@ -249,36 +258,59 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
     const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
     const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
     const int pitch = L.blur_pitch;
-    unsigned* W = s_win_all + warp * (EF_BW_INT * EF_BW_INT);
-    const int wx0 = k.x - EF_BW_HALF, wy0 = k.y - EF_BW_HALF;
+    unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);
+    const int gx0 = (k.x - EF_BW_HALF) & ~15, wy0 = k.y - EF_BW_HALF;
 
-    // pixels (zero outside the image) into W[j+1][i+1]; first row / column of the integral are zero
-    for (int j = lane; j < EF_BW_INT; j += 32) { W[j] = 0; W[j * EF_BW_INT] = 0; }
-    for (int j = 0; j < EF_BW_PIX; j++) {
-        const int gy = wy0 + j;
-        const bool rowin = gy >= 0 && gy < L.h;
-        for (int c = lane; c < EF_BW_PIX; c += 32) {
-            const int gx = wx0 + c;
-            unsigned v = 0;
-            if (rowin && gx >= 0 && gx < L.w) v = img[(size_t)gy * pitch + gx];
-            W[(j + 1) * EF_BW_INT + c + 1] = v;
+    // ---- 1. rows -> row prefixes.  Entry (r, a) of the row-prefix array is stored at P[r+1][a+1].
+    for (int j = lane; j < EF_BW_WORDS; j += 32) W[j] = 0;                 // P[0][*] = 0
+    {
+        const int c = lane & 3, g = lane >> 2;
+        const int gxc = gx0 + 16 * c;
+        const bool colok = gxc >= 0 && gxc + 15 < pitch;
+#pragma unroll
+        for (int it = 0; it < EF_BW_ROWS / 8; it++) {
+            const int r = 8 * it + g, gy = wy0 + r;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (colok && gy >= 0 && gy < L.h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
+            // inclusive prefix of the 16 bytes, two 16-bit lanes per register: q[m] = (prefix[2m], prefix[2m+1])
+            unsigned q[8];
+            unsigned run = 0;
+            const unsigned wv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const unsigned wd = wv[m >> 1];
+                const unsigned b0 = (wd >> (16 * (m & 1))) & 0xffu, b1 = (wd >> (16 * (m & 1) + 8)) & 0xffu;
+                const unsigned p0 = run + b0;
+                run = p0 + b1;
+                q[m] = p0 | (run << 16);
+            }
+            // exclusive scan of the chunk totals over the 4 lanes of the row
+            unsigned tot = run;
+            unsigned u = __shfl_up_sync(0xffffffffu, tot, 1); if (c >= 1) tot += u;
+            u = __shfl_up_sync(0xffffffffu, tot, 2); if (c >= 2) tot += u;
+            const unsigned base = (tot - run) * 0x10001u;
+            unsigned* dst = W + (r + 1) * EF_BW_WORDS + 8 * c + 1;         // halfword (r+1)*PITCH + 16c + 2 = entry a+1 of a = 16c
+#pragma unroll
+            for (int m = 0; m < 8; m++) dst[m] = q[m] + base;             // no carry between the halves: every prefix is < 64 * 255
+            if (c == 0) dst[-1] = 0;                                       // entry a = 0 (halfword 1) and the unused halfword 0
         }
     }
     __syncwarp();
-    // column prefix (lane <-> column), then row prefix (lane <-> row)
-    for (int c = lane; c < EF_BW_PIX; c += 32) {
-        unsigned run = 0;
-        for (int j = 1; j <= EF_BW_PIX; j++) { run += W[j * EF_BW_INT + c + 1]; W[j * EF_BW_INT + c + 1] = run; }
+    // ---- 2. column prefix, modulo 2^16 per halfword
+    if (lane < EF_BW_WORDS) {
+        unsigned lo = 0, hi = 0;
+#pragma unroll 8
+        for (int r = 1; r <= EF_BW_ROWS; r++) {
+            const unsigned wd = W[r * EF_BW_WORDS + lane];
+            lo += wd & 0xffffu; hi += wd >> 16;
+            W[r * EF_BW_WORDS + lane] = (lo & 0xffffu) | (hi << 16);
+        }
     }
-    __syncwarp();
-    for (int j = 1 + lane; j <= EF_BW_PIX; j += 32) {
-        unsigned run = 0;
-        for (int c = 1; c <= EF_BW_PIX; c++) { run += W[j * EF_BW_INT + c]; W[j * EF_BW_INT + c] = run; }
-    }
+    if (lane == 0) { unsigned lo = 0, hi = 0; for (int r = 1; r <= EF_BW_ROWS; r++) { const unsigned wd = W[r * EF_BW_WORDS + 32]; lo += wd & 0xffffu; hi += wd >> 16; W[r * EF_BW_WORDS + 32] = (lo & 0xffffu) | (hi << 16); } }
     __syncwarp();
 
     const EfBadAffine a = ef_bad_affine((float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, L.w, L.h);
-    EfWindowIntegral I; I.W = W; I.wx0 = wx0; I.wy0 = wy0; I.pitch = EF_BW_INT;
+    EfWindowIntegral16 I; I.P = reinterpret_cast<const unsigned short*>(W); I.gx0 = gx0; I.wy0 = wy0;
     uint8_t* out = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch;
     ef_bad_describe(I, a, t, p.desc_bytes * 8, L.w, L.h, out, lane);
 }
@@ -286,7 +318,7 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
 void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
 {
     if (p.total_kpt_blocks <= 0) return;
-    const size_t smem = (size_t)EF_DESC_WARPS * EF_BW_INT * EF_BW_INT * sizeof(unsigned);
+    const size_t smem = (size_t)EF_DESC_WARPS * (EF_BW_ROWS + 1) * EF_BW_WORDS * sizeof(unsigned);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ef_bad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

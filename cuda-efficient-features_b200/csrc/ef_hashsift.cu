@@ -69,7 +69,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                                                 const EfHashSiftTables& t, EfSiftWarpSmem& sm, uint8_t* out128, bool store)
 {
     const int lane = threadIdx.x & 31, hl = lane & 15, k = lane >> 4;
-    uint8_t* patch = sm.patch[k];
+    uint8_t* __restrict__ patch = sm.patch[k];
     // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
     {
         const float PI_1_0F = 3.14159274f;
@@ -80,13 +80,13 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const float sint = s * (angle >= 0 ? ef_libm::sinf_glibc(theta) : 0.f);
         const float M00 = +cost, M01 = -sint, M02 = (-cost + sint) * 32.f / 2.f + kx;
         const float M10 = +sint, M11 = +cost, M12 = (-sint - cost) * 32.f / 2.f + ky;
-        const uint8_t* base = img;
+        const uint8_t* __restrict__ base = img;
         int bpitch = pitch, ox = 0, oy = 0;
         if (STAGED) {
             // 48 rows x 64 bytes (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy
             const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - EF_SIFT_WIN / 2;
             const int gx0 = wx0 & ~15;
-            uint8_t* win = reinterpret_cast<uint8_t*>(sm.rec[k]);
+            uint8_t* __restrict__ win = reinterpret_cast<uint8_t*>(sm.rec[k]);
             const int gxc = gx0 + 16 * (hl & 3);
             const bool colok = gxc >= 0 && gxc + 15 < pitch;
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 const int ui = (int)floorf(u);
                 const int vi = (int)floorf(v);
                 if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
-                    const uint8_t* q = base + (vi - oy) * bpitch + (ui - ox);
+                    const uint8_t* __restrict__ q = base + (vi - oy) * bpitch + (ui - ox);
                     const float du = u - (float)ui;
                     const float dv = v - (float)vi;
                     const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
@@ -127,12 +127,12 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     __syncwarp();
     // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu)
     {
-        float* magp = sm.rec[k] + k;
-        float* ofp = sm.rec[k] + EF_SIFT_REC + k;
+        float* __restrict__ magp = sm.rec[k] + k;
+        float* __restrict__ ofp = sm.rec[k] + EF_SIFT_REC + k;
         int x = hl, y = 0;
 #pragma unroll 8
         for (int i = hl; i < 900; i += 16) {
-            const uint8_t* c = patch + (y + 1) * 32 + x + 1;
+            const uint8_t* __restrict__ c = patch + (y + 1) * 32 + x + 1;
             const int dxi = (int)c[1] - (int)c[-1];
             const int dyi = (int)c[-32] - (int)c[32];
             const float2 e = __ldg(t.grad_table + (dyi + 255) * 511 + (dxi + 255));
@@ -148,12 +148,13 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     // ---- trilinear histogram (hash_sift.cpp:233-290); cell (rb, cb) in 1..4
     {
         const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
-        const float* mp = sm.rec[k] + k;
-        const unsigned* op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
-        float* hc = sm.hist + lane;
+        const float* __restrict__ mp = sm.rec[k] + k;
+        const unsigned* __restrict__ op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
+        float* __restrict__ hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
         // Out-of-patch visits (rows/columns outside 0..29 for the border cells) are not branched around: they read record 0 and
         // add +0.0f, which leaves every (non-negative) accumulator unchanged -- the warp executes the iteration anyway.
+        // Per patch row: first the 16 shares (loads + arithmetic, independent -> pipelined), then the 16 ordered read-modify-writes.
 #pragma unroll
         for (int rseg = 0; rseg < 2; rseg++) {
             for (int iy = 0; iy < 8; iy++) {
@@ -161,29 +162,32 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 const bool rowok = (unsigned)y < 30u;
                 const float rf = 0.125f * (float)iy;
                 const int rowidx = y * 30 + 2 * (y >> 3) + xb;
+                float vo0[16], vo1[16];
+                unsigned hoff[16];
 #pragma unroll
-                for (int cseg = 0; cseg < 2; cseg++) {
+                for (int xo = 0; xo < 16; xo++) {
+                    const int cseg = xo >> 3, ix = xo & 7;
+                    const bool ok = rowok && (unsigned)(xb + xo) < 30u;
+                    const int idx = ok ? rowidx + xo : 0;
+                    const float mg = mp[idx];
+                    const unsigned ob = op[idx];
+                    const float mag = ok ? fabsf(mg) : 0.f;
+                    hoff[xo] = ((ob >> 30) | ((__float_as_uint(mg) >> 31) << 2)) * 32u;
+                    const float of = __uint_as_float(ob & 0x3fffffffu);
+                    // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
+                    const float v1 = rf * mag;
+                    const float vr = rseg == 0 ? v1 : mag - v1;
+                    const float c1 = (0.125f * (float)ix) * vr;
+                    const float vc = cseg == 0 ? c1 : vr - c1;
+                    vo1[xo] = of * vc;
+                    vo0[xo] = vc - vo1[xo];
+                }
 #pragma unroll
-                    for (int ix = 0; ix < 8; ix++) {
-                        const int xo = 8 * cseg + ix;
-                        const bool ok = rowok && (unsigned)(xb + xo) < 30u;
-                        const int idx = ok ? rowidx + xo : 0;
-                        const float mg = mp[idx];
-                        const unsigned ob = op[idx];
-                        const float mag = ok ? fabsf(mg) : 0.f;
-                        const unsigned oi = (ob >> 30) | ((__float_as_uint(mg) >> 31) << 2);
-                        const float of = __uint_as_float(ob & 0x3fffffffu);
-                        // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
-                        const float v1 = rf * mag;
-                        const float vr = rseg == 0 ? v1 : mag - v1;
-                        const float c1 = (0.125f * (float)ix) * vr;
-                        const float vc = cseg == 0 ? c1 : vr - c1;
-                        const float vo1 = of * vc, vo0 = vc - vo1;
-                        float* h0 = hc + oi * 32;
-                        const float a0 = h0[0], a1 = h0[32];
-                        h0[0] = a0 + vo0;
-                        h0[32] = a1 + vo1;
-                    }
+                for (int xo = 0; xo < 16; xo++) {
+                    float* h0 = hc + hoff[xo];
+                    const float a0 = h0[0], a1 = h0[32];
+                    h0[0] = a0 + vo0[xo];
+                    h0[32] = a1 + vo1[xo];
                 }
             }
         }
