@@ -152,13 +152,13 @@ struct EfGlobalIntegral { // (h+1) x (w+1) uint32 integral image of the whole fr
     __device__ __forceinline__ unsigned at(int y, int x) const { return __ldg(I + (size_t)y * iw + x); }
     __device__ __forceinline__ unsigned box(int y0, int x0, int y1, int x1) const { return at(y0, x0) + at(y1, x1) - at(y0, x1) - at(y1, x0); }
 };
-// 16-bit modular integral of the 48-row window around a keypoint (ef_bad_pipe_kernel): P[r][a] (halfword r*PITCH + a + 1) =
-// sum over window rows < r of the bytes [0, a) of the 64-byte aligned row + a per-row constant that cancels in every box.
+// 16-bit modular integral of the 48-row window around a keypoint (ef_bad_pipe_kernel): P[r][a] (halfword r*PITCH + a) =
+// sum over window rows < r of the bytes [0, a) of the 64-byte aligned row segment, a in [0, 63].
 // Exact for boxes whose true sum is < 2^16, i.e. radius <= 7 (15 x 15 x 255 = 57375): the detectAndCompute path (size 31, scale 1).
-#define EF_BW_PITCH 66 // halfwords per row: 65 entries + 1 so that entry pairs are word aligned; 33 words (odd) spreads the banks
+#define EF_BW_PITCH 66 // halfwords per row: 64 entries (32 words) + one pad word: 33 words (odd) spreads the banks
 struct EfWindowIntegral16 {
     const unsigned short* P; int gx0, wy0;
-    __device__ __forceinline__ unsigned at(int y, int x) const { return P[(y - wy0) * EF_BW_PITCH + (x - gx0) + 1]; }
+    __device__ __forceinline__ unsigned at(int y, int x) const { return P[(y - wy0) * EF_BW_PITCH + (x - gx0)]; }
     __device__ __forceinline__ unsigned box(int y0, int x0, int y1, int x1) const { return (at(y0, x0) + at(y1, x1) - at(y0, x1) - at(y1, x0)) & 0xffffu; }
 };
 
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
     unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);
     const int gx0 = (k.x - EF_BW_HALF) & ~15, wy0 = k.y - EF_BW_HALF;
 
-    // ---- 1. rows -> row prefixes.  Entry (r, a) of the row-prefix array is stored at P[r+1][a+1].
-    for (int j = lane; j < EF_BW_WORDS; j += 32) W[j] = 0;                 // P[0][*] = 0
+    // ---- 1. rows -> exclusive row prefixes: P[r+1][a] = sum of the bytes [0, a) of window row r (before the column pass)
+    W[lane] = 0;                                                           // P[0][*] = 0
     {
         const int c = lane & 3, g = lane >> 2;
         const int gxc = gx0 + 16 * c;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
             const int r = 8 * it + g, gy = wy0 + r;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (colok && gy >= 0 && gy < L.h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
-            // inclusive prefix of the 16 bytes, two 16-bit lanes per register: q[m] = (prefix[2m], prefix[2m+1])
+            // exclusive prefix of the 16 bytes, two 16-bit lanes per register: q[m] = (prefix[2m], prefix[2m+1])
             unsigned q[8];
             unsigned run = 0;
             const unsigned wv[4] = { v.x, v.y, v.z, v.w };
@@ -280,24 +280,25 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
             for (int m = 0; m < 8; m++) {
                 const unsigned wd = wv[m >> 1];
                 const unsigned b0 = (wd >> (16 * (m & 1))) & 0xffu, b1 = (wd >> (16 * (m & 1) + 8)) & 0xffu;
-                const unsigned p0 = run + b0;
-                run = p0 + b1;
-                q[m] = p0 | (run << 16);
+                const unsigned p1 = run + b0;
+                q[m] = run | (p1 << 16);
+                run = p1 + b1;
             }
             // exclusive scan of the chunk totals over the 4 lanes of the row
             unsigned tot = run;
             unsigned u = __shfl_up_sync(0xffffffffu, tot, 1); if (c >= 1) tot += u;
             u = __shfl_up_sync(0xffffffffu, tot, 2); if (c >= 2) tot += u;
             const unsigned base = (tot - run) * 0x10001u;
-            unsigned* dst = W + (r + 1) * EF_BW_WORDS + 8 * c + 1;         // halfword (r+1)*PITCH + 16c + 2 = entry a+1 of a = 16c
+            uint4* dst = reinterpret_cast<uint4*>(W + (r + 1) * EF_BW_WORDS + 8 * c);
+            // no carry between the halves: every prefix is < 64 * 255.  (rows are 132 bytes apart: 4-byte aligned stores only)
+            unsigned* d32 = reinterpret_cast<unsigned*>(dst);
 #pragma unroll
-            for (int m = 0; m < 8; m++) dst[m] = q[m] + base;             // no carry between the halves: every prefix is < 64 * 255
-            if (c == 0) dst[-1] = 0;                                       // entry a = 0 (halfword 1) and the unused halfword 0
+            for (int m = 0; m < 8; m++) d32[m] = q[m] + base;
         }
     }
     __syncwarp();
-    // ---- 2. column prefix, modulo 2^16 per halfword
-    if (lane < EF_BW_WORDS) {
+    // ---- 2. column prefix, modulo 2^16 per halfword: one 32-bit word (two columns) per lane
+    {
         unsigned lo = 0, hi = 0;
 #pragma unroll 8
         for (int r = 1; r <= EF_BW_ROWS; r++) {
@@ -306,7 +307,6 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
             W[r * EF_BW_WORDS + lane] = (lo & 0xffffu) | (hi << 16);
         }
     }
-    if (lane == 0) { unsigned lo = 0, hi = 0; for (int r = 1; r <= EF_BW_ROWS; r++) { const unsigned wd = W[r * EF_BW_WORDS + 32]; lo += wd & 0xffffu; hi += wd >> 16; W[r * EF_BW_WORDS + 32] = (lo & 0xffffu) | (hi << 16); } }
     __syncwarp();
 
     const EfBadAffine a = ef_bad_affine((float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, L.w, L.h);

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
 {
     __shared__ __align__(16) unsigned s_h0[SC_ROWS][SC_HW];
     __shared__ __align__(16) unsigned s_h1[SC_ROWS][SC_HW];
-    __shared__ __align__(16) float2 s_grad[SC_GROWS][SC_ROWS];
+    __shared__ __align__(16) unsigned s_grad[SC_GROWS][SC_ROWS]; // Sobel sums (dx, dy) of tile-local pixel (col, row+1) as an fp16 pair: exact integers
     __shared__ __align__(16) float s_resp[EF_TILE][EF_TILE];
     __shared__ unsigned short s_list[2][EF_TILE * EF_TILE / 2]; // corners with even / odd tile column
     __shared__ int s_n[2];
@@ -335,9 +335,10 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
     const int n = n_even + n_odd;
 
     if (n > 0) {
-        // ---- Sobel gradients of tile-local rows/columns 1..38 (cuda_efficient_features.cu:116-128), two pixels per thread:
-        //      dx = colsum(x+1) - colsum(x-1), colsum = v(y-1) + 2 v(y) + v(y+1); dy likewise with rows
-        const float SCALE = 1.f / (4 * 7 * 255);
+        // ---- Sobel sums of tile-local rows/columns 1..38 (cuda_efficient_features.cu:116-128), two pixels per thread:
+        //      dx = colsum(x+1) - colsum(x-1), colsum = v(y-1) + 2 v(y) + v(y+1); dy likewise with rows.  Kept as fp16 integer
+        //      pairs (|d| <= 1020, exact); the scale 1/(4*7*255) is applied where the gradient is used, exactly as
+        //      SCALE * (float)d in the reference.
         const unsigned twou = 0x40004000u;
         const __half2 two = *reinterpret_cast<const __half2*>(&twou);
         for (int i = tid; i < SC_GROWS * 20; i += 256) {
@@ -354,17 +355,18 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             const __half2 up = __hfma2(two, H2(bm), __hadd2(H2(am), H2(cm)));
 #undef H2
             const __half2 dx2 = __hsub2(right, left), dy2 = __hsub2(down, up);
-            float4 g;
-            g.x = SCALE * __low2float(dx2); g.y = SCALE * __low2float(dy2);
-            g.z = SCALE * __high2float(dx2); g.w = SCALE * __high2float(dy2);
-            *reinterpret_cast<float4*>(&s_grad[row][2 * pr]) = g;
+            const unsigned ux = *reinterpret_cast<const unsigned*>(&dx2), uy = *reinterpret_cast<const unsigned*>(&dy2);
+            // (dx, dy) of the first pixel, (dx, dy) of the second
+            *reinterpret_cast<uint2*>(&s_grad[row][2 * pr]) = make_uint2(__byte_perm(ux, uy, 0x5410), __byte_perm(ux, uy, 0x7632));
         }
         __syncthreads();
         // ---- Harris, raster order over the 7x7 block with the reference's contraction:
-        //      sxx = fmaf(gx,gx,sxx), sxy = fmaf(gx,gy,sxy), syy = fmaf(gy,gy,syy) per tap.  (sxx, syy) advance together in one
-        //      packed FFMA2 (fma.rn.f32x2, per-lane IEEE).  The window columns are cx+1 .. cx+7 of s_grad: for an odd cx they
-        //      start on a 16-byte boundary (3 x LDS.128 + LDS.64 per row), for an even cx one tap later -- the two parity lists
-        //      keep every warp on one of the two layouts.
+        //      g = SCALE * (float)d; sxx = fmaf(gx,gx,sxx), sxy = fmaf(gx,gy,sxy), syy = fmaf(gy,gy,syy) per tap.  (gx, gy) is one
+        //      packed multiply and (sxx, syy) advance together in one packed FFMA2 (mul/fma.rn.f32x2, per-lane IEEE).  The window
+        //      columns are cx+1 .. cx+7 of s_grad: for an odd cx they start on an 8-byte boundary (3 x LDS.64 + LDS.32 per row),
+        //      for an even cx one tap later -- the two parity lists keep every warp on one of the two layouts.
+        const float SCALE = 1.f / (4 * 7 * 255);
+        const unsigned long long scale2 = ef_pack2(SCALE, SCALE);
         const int npad_even = (n_even + 31) & ~31;       // odd-list work starts on a fresh warp
         for (int i = tid; i < npad_even + n_odd; i += 256) {
             const bool odd = i >= npad_even;
@@ -374,26 +376,28 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             const int cx = pos & 31, cy = pos >> 5;
             unsigned long long acc = 0ull; // (sxx, syy)
             float sxy = 0.f;
-#define EF_TAP(G) { const unsigned long long g_ = (G); float gx_, gy_; \
+#define EF_TAP(D) { const unsigned d_ = (D); \
+                    const __half2 h_ = *reinterpret_cast<const __half2*>(&d_); \
+                    const unsigned long long g_ = ef_mul2(ef_pack2(__low2float(h_), __high2float(h_)), scale2); float gx_, gy_; \
                     asm("mov.b64 {%0, %1}, %2;" : "=f"(gx_), "=f"(gy_) : "l"(g_)); \
                     asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(g_)); \
                     sxy = fmaf(gx_, gy_, sxy); }
             if (odd) {
 #pragma unroll
                 for (int iy = 0; iy < 7; iy++) {
-                    const float2* row = &s_grad[cy + iy][cx + 1];
-                    const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(row), q1 = *reinterpret_cast<const ulonglong2*>(row + 2),
-                                     q2 = *reinterpret_cast<const ulonglong2*>(row + 4);
-                    const unsigned long long q3 = *reinterpret_cast<const unsigned long long*>(row + 6);
+                    const unsigned* row = &s_grad[cy + iy][cx + 1];
+                    const uint2 q0 = *reinterpret_cast<const uint2*>(row), q1 = *reinterpret_cast<const uint2*>(row + 2),
+                                q2 = *reinterpret_cast<const uint2*>(row + 4);
+                    const unsigned q3 = row[6];
                     EF_TAP(q0.x) EF_TAP(q0.y) EF_TAP(q1.x) EF_TAP(q1.y) EF_TAP(q2.x) EF_TAP(q2.y) EF_TAP(q3)
                 }
             } else {
 #pragma unroll
                 for (int iy = 0; iy < 7; iy++) {
-                    const float2* row = &s_grad[cy + iy][cx + 1];
-                    const unsigned long long q0 = *reinterpret_cast<const unsigned long long*>(row);
-                    const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(row + 1), q2 = *reinterpret_cast<const ulonglong2*>(row + 3),
-                                     q3 = *reinterpret_cast<const ulonglong2*>(row + 5);
+                    const unsigned* row = &s_grad[cy + iy][cx + 1];
+                    const unsigned q0 = row[0];
+                    const uint2 q1 = *reinterpret_cast<const uint2*>(row + 1), q2 = *reinterpret_cast<const uint2*>(row + 3),
+                                q3 = *reinterpret_cast<const uint2*>(row + 5);
                     EF_TAP(q0) EF_TAP(q1.x) EF_TAP(q1.y) EF_TAP(q2.x) EF_TAP(q2.y) EF_TAP(q3.x) EF_TAP(q3.y)
                 }
             }
@@ -862,6 +866,7 @@ __constant__ int c_umax[16] = { 15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 
 
 __global__ void __launch_bounds__(256) ef_angle_pack_kernel(const __grid_constant__ EfPipe p)
 {
+    __shared__ int s_m[EF_KPTS_PER_CTA][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
@@ -874,40 +879,50 @@ __global__ void __launch_bounds__(256) ef_angle_pack_kernel(const __grid_constan
 
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::kpt_block_start);
     const EfLevel& L = p.lv[level];
-    const int i = (blockIdx.x - L.kpt_block_start) * EF_KPTS_PER_CTA + warp;
-    if (i >= ctr[level].selected) return;
-    int offset = 0;
-    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
-
+    const int nsel = ctr[level].selected;
+    const int i0 = (blockIdx.x - L.kpt_block_start) * EF_KPTS_PER_CTA;
+    if (i0 >= nsel) return;                                   // CTA-uniform
     EfSelected* sel = reinterpret_cast<EfSelected*>(ef_ws(p, frame, L.sel_off));
-    const EfSelected k = sel[i];
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
-    const uint8_t* c = img + (size_t)k.y * pitch + k.x;
 
-    // IC_Angle, cuda_efficient_features.cu:141-172: lane <-> dx = lane-15
-    int m01 = 0, m10 = 0;
-    const int dx = lane - EF_HALF_PATCH;
-    if (lane < 31) {
-        m10 = dx * (int)c[dx];
-        const int adx = abs(dx);
-        for (int dy = 1; dy <= EF_HALF_PATCH; dy++) {
-            if (adx <= c_umax[dy]) {
-                const int vT = c[-(ptrdiff_t)dy * pitch + dx];
-                const int vB = c[(ptrdiff_t)dy * pitch + dx];
-                m01 += dy * (vB - vT);
-                m10 += dx * (vB + vT);
+    // IC_Angle, cuda_efficient_features.cu:141-172: warp = keypoint, lane <-> dx = lane-15; integer moments (exact)
+    if (i0 + warp < nsel) {
+        const EfSelected k = sel[i0 + warp];
+        const uint8_t* c = img + (size_t)k.y * pitch + k.x;
+        int m01 = 0, m10 = 0;
+        const int dx = lane - EF_HALF_PATCH;
+        if (lane < 31) {
+            m10 = dx * (int)c[dx];
+            const int adx = abs(dx);
+            const uint8_t* pT = c + dx;
+            const uint8_t* pB = c + dx;
+#pragma unroll
+            for (int dy = 1; dy <= EF_HALF_PATCH; dy++) {
+                pT -= pitch; pB += pitch;
+                if (adx <= c_umax[dy]) {
+                    const int vT = *pT, vB = *pB;
+                    m01 += dy * (vB - vT);
+                    m10 += dx * (vB + vT);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        }
+        if (lane == 0) { s_m[warp][0] = m01; s_m[warp][1] = m10; }
     }
-    if (lane == 0) {
+    __syncthreads();
+    // one thread per keypoint of the CTA: the double-precision atan2 runs once per CTA instead of once per warp
+    if (tid < EF_KPTS_PER_CTA && i0 + tid < nsel) {
+        const int i = i0 + tid;
+        const EfSelected k = sel[i];
+        int offset = 0;
+        for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
         // canonical: atan2 in double, rounded once (the reference's CUDA atan2f is <= 2 ulp)
-        float angle = (float)atan2((double)(float)m01, (double)(float)m10);
+        float angle = (float)atan2((double)(float)s_m[tid][0], (double)(float)s_m[tid][1]);
         const float PI = 3.14159274f; // (float)CV_PI
         if (angle < 0) angle += 2.f * PI;
         angle = (180.f / PI) * angle;

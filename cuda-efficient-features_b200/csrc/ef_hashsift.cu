@@ -31,7 +31,8 @@
 #define EF_SIFT_REC 916                 // floats per record array (30x30 skewed needs 906)
 #define EF_SIFT_BLK (2 * EF_SIFT_REC)   // record block of one keypoint (16-byte multiple): magnitudes then fractions
 #define EF_SIFT_WIN 48                  // staged window edge (pixels); every sample of a size-31 patch lies in [k-22, k+22]
-#define EF_SIFT_WIN_PITCH 80            // bytes: 64 loaded (48 pixels + up to 15 alignment bytes), 20-word pitch spreads the banks
+#define EF_SIFT_WIN_PITCH 136           // bytes per staged row: 64 pixels (48 + up to 15 alignment bytes), TWO bytes each -- entry x holds
+                                        // (pixel x, pixel x+1), so a bilinear sample is two 16-bit loads; 34-word pitch spreads the banks
 
 struct EfSiftWarpSmem {                 // per warp = 2 keypoints
     float hist[9 * 32];                 // [bin 0..8][lane]
@@ -83,7 +84,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const uint8_t* __restrict__ base = img;
         int bpitch = pitch, ox = 0, oy = 0;
         if (STAGED) {
-            // 48 rows x 64 bytes (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy
+            // 48 rows x 64 pixels (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy; stored as
+            // overlapping pixel pairs (x, x+1): the first pixel of the next chunk comes from the neighbouring lane
             const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - EF_SIFT_WIN / 2;
             const int gx0 = wx0 & ~15;
             uint8_t* __restrict__ win = reinterpret_cast<uint8_t*>(sm.rec[k]);
@@ -94,7 +96,12 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 const int row = 4 * it + (hl >> 2), gy = wy0 + row;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
-                *reinterpret_cast<uint4*>(win + row * EF_SIFT_WIN_PITCH + 16 * (hl & 3)) = v;
+                const unsigned nx = __shfl_down_sync(0xffffffffu, v.x, 1); // chunk 3: pixel 64 is never sampled
+                uint2* dst = reinterpret_cast<uint2*>(win + row * EF_SIFT_WIN_PITCH + 32 * (hl & 3));
+                dst[0] = make_uint2(__byte_perm(v.x, 0, 0x2110), __byte_perm(v.x, v.y, 0x4332));
+                dst[1] = make_uint2(__byte_perm(v.y, 0, 0x2110), __byte_perm(v.y, v.z, 0x4332));
+                dst[2] = make_uint2(__byte_perm(v.z, 0, 0x2110), __byte_perm(v.z, v.w, 0x4332));
+                dst[3] = make_uint2(__byte_perm(v.w, 0, 0x2110), __byte_perm(v.w, nx, 0x4332));
             }
             __syncwarp();
             base = win; bpitch = EF_SIFT_WIN_PITCH; ox = gx0; oy = wy0;
@@ -112,11 +119,19 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 const int ui = (int)floorf(u);
                 const int vi = (int)floorf(v);
                 if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
-                    const uint8_t* __restrict__ q = base + (vi - oy) * bpitch + (ui - ox);
                     const float du = u - (float)ui;
                     const float dv = v - (float)vi;
-                    const float tmp0 = (1 - du) * (float)q[0] + du * (float)q[1];
-                    const float tmp1 = (1 - du) * (float)q[bpitch] + du * (float)q[bpitch + 1];
+                    float q00, q01, q10, q11;
+                    if (STAGED) {
+                        const unsigned short* __restrict__ q = reinterpret_cast<const unsigned short*>(base + (vi - oy) * EF_SIFT_WIN_PITCH) + (ui - ox);
+                        const unsigned t0 = q[0], t1 = q[EF_SIFT_WIN_PITCH / 2];
+                        q00 = (float)(t0 & 0xffu); q01 = (float)(t0 >> 8); q10 = (float)(t1 & 0xffu); q11 = (float)(t1 >> 8);
+                    } else {
+                        const uint8_t* __restrict__ q = base + (vi - oy) * bpitch + (ui - ox);
+                        q00 = (float)q[0]; q01 = (float)q[1]; q10 = (float)q[bpitch]; q11 = (float)q[bpitch + 1];
+                    }
+                    const float tmp0 = (1 - du) * q00 + du * q01;
+                    const float tmp1 = (1 - du) * q10 + du * q11;
                     const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
                     dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
                 }
@@ -125,22 +140,33 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         }
     }
     __syncwarp();
-    // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu)
+    // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu).
+    //      Eight pixels per lane and step, in three explicit stages (patch reads, table gathers, record writes) so that the
+    //      eight gathers are in flight together instead of one global round trip per pixel.
     {
         float* __restrict__ magp = sm.rec[k] + k;
         float* __restrict__ ofp = sm.rec[k] + EF_SIFT_REC + k;
-        int x = hl, y = 0;
-#pragma unroll 8
-        for (int i = hl; i < 900; i += 16) {
-            const uint8_t* __restrict__ c = patch + (y + 1) * 32 + x + 1;
-            const int dxi = (int)c[1] - (int)c[-1];
-            const int dyi = (int)c[-32] - (int)c[32];
-            const float2 e = __ldg(t.grad_table + (dyi + 255) * 511 + (dxi + 255));
-            const int idx = i + 2 * (y >> 3);
-            magp[idx] = __ldg(t.exp_table + i) * e.x;
-            ofp[idx] = e.y;
-            x += 16;
-            if (x >= 30) { x -= 30; y++; }
+        for (int i0 = hl; i0 < 900; i0 += 16 * 8) {
+            int tix[8], rix[8], pix[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = min(i0 + 16 * u, 899);          // lanes past the end repeat pixel 899 (their writes are skipped)
+                const int y = (i * 1093) >> 15, x = i - 30 * y; // i / 30 for i < 1024
+                const uint8_t* c = patch + (y + 1) * 32 + x + 1;
+                const int dxi = (int)c[1] - (int)c[-1];
+                const int dyi = (int)c[-32] - (int)c[32];
+                tix[u] = (dyi + 255) * 511 + (dxi + 255);
+                rix[u] = i + 2 * (y >> 3);
+                pix[u] = i;
+            }
+            float2 e[8];
+            float ew[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { e[u] = __ldg(t.grad_table + tix[u]); ew[u] = __ldg(t.exp_table + pix[u]); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (i0 + 16 * u < 900) { magp[rix[u]] = ew[u] * e[u].x; ofp[rix[u]] = e[u].y; }
+            }
         }
     }
     for (int b = 0; b < 9; b++) sm.hist[b * 32 + lane] = 0.f;
