@@ -241,16 +241,23 @@ def main():
         ach = alg[stage] * B / (per_call[stage] * 1e-3) / 1e9 if per_call[stage] > 0 else 0.0
         return {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "ms_per_launch_group": per_call[stage], "algorithmic_bytes_per_step": alg[stage] * B}
+    # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch group from the committed ncu capture (profiles/traffic.json,
+    # written by tools/ncu_summary.py for a batch of `frames` frames), rescaled to this run's batch
     traffic_file = ROOT / "profiles" / "traffic.json"
-    roofline = roof(dom)
-    roofline_pyr = roof("pyramid")
+    tr = {}
     if traffic_file.exists():
         try:
             tr = json.loads(traffic_file.read_text())
-            roofline["traffic"] = tr.get(dom)
-            roofline_pyr["traffic"] = tr.get("pyramid")
         except Exception:
-            pass
+            tr = {}
+    def with_traffic(r):
+        v = tr.get(("describe_bad" if (r["kernel"] == "describe" and dtype_id < 2) else r["kernel"]))
+        if isinstance(v, (int, float)) and tr.get("_frames"):
+            r["traffic"] = v * B / float(tr["_frames"])
+        return r
+    roofline = with_traffic(roof(dom))
+    roofline_pyr = with_traffic(roof("pyramid"))
+    rooflines = {st: with_traffic(roof(st)) for st in per_call if per_call[st] > 0}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -263,7 +270,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
             "data": "synthetic", "config": config, "frames_per_s": value * 1e6 / (W * H), "keypoints_per_s": kps,
             "keypoints_per_frame": n_frame, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "roofline_pyramid": roofline_pyr, "stage_ms_per_step": per_call, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "roofline_pyramid": roofline_pyr, "stage_ms_per_step": per_call,
+            "stage_roofline_frac": {k: round(v["frac"], 5) for k, v in rooflines.items()}, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

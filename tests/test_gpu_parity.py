@@ -181,3 +181,71 @@ def test_errors(torch_cuda):
         ef.detectAndComputeRaw(torch.zeros((1000, 1000), dtype=torch.uint8, device="cuda"))
     kp, desc = ef.detectAndComputeAsync(img)  # blank image: zero keypoints, like the reference's release()
     assert kp.shape[1] == 0 and desc.shape[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: 4K / 40 000 requested keypoints against the oracle, 8K through properties
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype_name", ["HASH_SIFT_512", "BAD_512"])
+def test_full_size_4k_matches_oracle(torch_cuda, oracle, dtype_name):
+    """configs[1]/[2]/[4] geometry: 3840x2160, nfeatures 40000, r 15 -- bit-exact keypoints and descriptors"""
+    import efb200, efo
+    torch = torch_cuda
+    w, h, nfeat = 3840, 2160, 40000
+    img = oracle.synth_frame(util.SEED + 41, 0, w, h)
+    ef = make_ef(nfeatures=nfeat, dtype=getattr(efb200, dtype_name), max_width=w, max_height=h)
+    kp, desc = ef.detectAndComputeAsync(torch.from_numpy(img).cuda())
+    g = ef.convert(kp)
+    gd = desc.cpu().numpy()
+    ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(nfeatures=nfeat, desc_type=getattr(efo, dtype_name)))
+    o = util.oracle_to_struct(ok)
+    util.assert_keypoints_equal(g, o)
+    _, go = util.canon_keypoints(g)
+    _, oo = util.canon_keypoints(o)
+    assert np.array_equal(gd[go], od[oo])
+
+
+def nms_property_ok(k, radius, scales):
+    """no two keypoints of the same level closer than the radius in level coordinates (checked on the scaled coordinates with the
+    rounding slack of scalePoints: |x' - s x| < 1)"""
+    for octave in np.unique(k["octave"]):
+        s = float(scales[octave])
+        m = k[k["octave"] == octave]
+        xs, ys = m["x"].astype(np.float64) / s, m["y"].astype(np.float64) / s
+        order = np.argsort(ys)
+        xs, ys = xs[order], ys[order]
+        lim = radius - 2.0  # r minus the rounding slack of both points
+        for i in range(len(xs)):
+            j = i + 1
+            while j < len(xs) and ys[j] - ys[i] < lim:
+                if (xs[j] - xs[i]) ** 2 + (ys[j] - ys[i]) ** 2 < lim * lim:
+                    return False
+                j += 1
+    return True
+
+
+def test_8k_properties_and_determinism(torch_cuda):
+    """configs[3] geometry (7680x4320, HashSIFT-512, 40 000 keypoints): size-independent properties instead of the oracle --
+    every per-level quota binds at 8K (count == nfeatures), NMS spacing holds, the run is deterministic, and the batched call
+    returns for every frame exactly what the single-frame call returns."""
+    import efb200
+    torch = torch_cuda
+    w, h, nfeat = 7680, 4320, 40000
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    frames = torch.randint(0, 256, (2, h, w), dtype=torch.uint8, generator=gen).cuda()
+    ef = make_ef(nfeatures=nfeat, dtype=efb200.HASH_SIFT_512, max_width=w, max_height=h, max_batch=2)
+    kp1, d1 = ef.detectAndComputeAsync(frames[0])
+    kp2, d2 = ef.detectAndComputeAsync(frames[0])
+    assert kp1.shape[1] == nfeat, f"8K noise must fill every quota, got {kp1.shape[1]}"
+    assert torch.equal(kp1.view(torch.int32), kp2.view(torch.int32)) and torch.equal(d1, d2), "run-to-run determinism"
+    k = ef.convert(kp1)
+    scales = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    assert nms_property_ok(k, 15, scales)
+    assert (k["octave"] >= 0).all() and (k["octave"] < 8).all()
+    assert np.array_equal(np.sort(np.bincount(k["octave"], minlength=8))[::-1], np.bincount(k["octave"], minlength=8)), "quotas decrease with the level"
+    kpb, db, counts = ef.detectAndComputeBatchRaw(frames)
+    torch.cuda.synchronize()
+    assert int(counts[0]) == nfeat
+    assert torch.equal(kpb[0].view(torch.int32), kp1.contiguous().view(torch.int32)) and torch.equal(db[0], d1)
+    # frame 1 differs from frame 0 (no cross-frame leakage of workspace slots)
+    assert not torch.equal(db[1], db[0])

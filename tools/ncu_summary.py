@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 STAGE_OF = [("ef_resize", "pyramid"), ("ef_score", "score"), ("ef_nms", "nms"), ("ef_compact", "compact"), ("ef_select", "select"),
-            ("ef_angle_pack", "angle_pack"), ("ef_blur", "blur"), ("ef_hashsift_pipe", "describe"), ("ef_bad_pipe", "describe"),
+            ("ef_angle_pack", "angle_pack"), ("ef_blur", "blur"), ("ef_hashsift_pipe", "describe"), ("ef_bad_pipe", "describe_bad"),
             ("ef_hashsift_project", "project")]
 COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
@@ -59,7 +59,8 @@ def main():
         res = {}
         for stage, v in traffic.items():
             res[stage] = sum(v) if stage == "pyramid" else sum(v) / len(v)
-        res["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch group (one step of the captured bench command), from " + rep
+        res["_frames"] = int(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 8
+        res["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch group (one step of the captured bench command, _frames frames), from " + rep
         with open(traffic_path, "w") as f:
             json.dump(res, f, indent=1)
 
