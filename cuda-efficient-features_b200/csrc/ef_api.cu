@@ -51,6 +51,17 @@ void compute_geometry(int w, int h, float scaleFactor, int nlevels, int nfeature
     g.quota[nlevels - 1] = std::max(nfeatures - sum, 0);
 }
 
+// Capacity of a level's survivor list.  The reference sizes it 0.1 * area (CORNER_DENSITY, cuda_efficient_features.cpp:35,252).
+// NMS survivors are pairwise at least sqrt(r2) apart, i.e. at most ~1.155 / r2 of the pixels (hexagonal packing): below r = 4 that
+// bound exceeds 10 %, so the list is sized from it (+ a boundary term) and can never overflow: results always equal the oracle's.
+long surv_capacity(int w, int h, int r2)
+{
+    const double area = (double)w * h;
+    const double dens = r2 <= 1 ? 1.0 : std::min(1.0, 1.3 / (double)r2);
+    const double cap = std::max(0.1 * area, dens * area + 2.0 * (w + h));
+    return std::max(1l, lrint(std::min(area, cap)));
+}
+
 int desc_bytes_of(int t) { return (t == EF_BAD_256 || t == EF_HASH_SIFT_256) ? 32 : 64; }
 bool is_bad(int t) { return t == EF_BAD_256 || t == EF_BAD_512; }
 
@@ -204,7 +215,7 @@ void plan_workspace(ef_handle* h)
         q.blk_off = off; if (nb) off += ef_align_up((unsigned long long)ef_div_up(w, nb) * ef_div_up(hh, nb) * sizeof(EfBlockMax), 256);
         const unsigned long long tiles = (unsigned long long)ef_div_up(w, EF_TILE) * ef_div_up(hh, EF_TILE);
         q.mask_off = off; off += ef_align_up(tiles * EF_TILE * 4, 256);
-        const unsigned long long surv_cap = (unsigned long long)std::max(1l, lrint(0.1 * (double)w * hh));
+        const unsigned long long surv_cap = (unsigned long long)surv_capacity(w, hh, nms_geometry(p.nonmax_radius).r2);
         q.surv_off = off; off += ef_align_up(surv_cap * sizeof(EfSurvivor), 256);
         q.sel_off = off; off += ef_align_up((unsigned long long)p.nfeatures * sizeof(EfSelected), 256);
     }
@@ -354,6 +365,8 @@ int allocate(ef_handle* h)
     size_t total = 0;
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { total += bytes; return cudaMalloc(ptr, bytes ? bytes : 1); };
     EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
+    // row padding (columns w .. pitch) is read by the 16-byte window loads but never written: define it once
+    EF_CUDA(h, cudaMemset(h->d_ws, 0, (size_t)h->slot_bytes * p.max_batch));
     EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
     h->sift_rows = std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
     EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
@@ -364,6 +377,7 @@ int allocate(ef_handle* h)
     h->in_pitch = ef_align_up(p.max_width, 128);
     h->in_stride = h->in_pitch * p.max_height;
     EF_CUDA(h, alloc((void**)&h->d_in, h->in_stride * p.max_batch));
+    EF_CUDA(h, cudaMemset(h->d_in, 0, h->in_stride * p.max_batch));
     h->out_kpts_pitch = ef_align_up((size_t)p.nfeatures * 4, 128);
     h->out_kpts_stride = h->out_kpts_pitch * EF_ROWS_COUNT;
     EF_CUDA(h, alloc((void**)&h->d_out_kpts, h->out_kpts_stride * p.max_batch));
@@ -410,7 +424,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
         L.blk_w = ng.block ? ef_div_up(L.w, ng.block) : 0; L.blk_h = ng.block ? ef_div_up(L.h, ng.block) : 0;
         L.blur_tiles_x = ef_div_up(L.w, 64);
         L.quota = g.quota[l];
-        L.surv_cap = (int)std::max(1l, lrint(0.1 * (double)L.w * L.h)); // CORNER_DENSITY, cuda_efficient_features.cpp:35,252
+        L.surv_cap = (int)surv_capacity(L.w, L.h, ng.r2);
         L.scale = g.scale[l];
         if (l > 0) {
             L.rx = (float)(1.0 / ((double)L.w / g.w[l - 1]));
@@ -547,7 +561,7 @@ int ef_set_param(ef_handle* h, int id, double value)
     int rc = validate(q, why);
     if (rc != EF_OK) return fail(h, rc, why);
     const bool replan = q.nfeatures > h->prm.nfeatures || q.nlevels != h->prm.nlevels || q.scale_factor != h->prm.scale_factor ||
-                        nms_geometry(q.nonmax_radius).block != nms_geometry(h->prm.nonmax_radius).block;
+                        q.nonmax_radius != h->prm.nonmax_radius; // block-map and survivor-list capacities depend on the radius
     if (q.max_keypoints < q.nfeatures) q.max_keypoints = q.nfeatures;
     h->prm = q;
     if (replan) {

@@ -249,3 +249,106 @@ def test_8k_properties_and_determinism(torch_cuda):
     assert torch.equal(kpb[0].view(torch.int32), kp1.contiguous().view(torch.int32)) and torch.equal(db[0], d1)
     # frame 1 differs from frame 0 (no cross-frame leakage of workspace slots)
     assert not torch.equal(db[1], db[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases: sizes, alignments, parameter boundaries of the tiled kernels (all against the oracle)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(32, 32), (33, 47), (64, 35), (129, 130), (255, 257), (771, 99)])
+def test_small_and_odd_sizes(torch_cuda, oracle, w, h):
+    """minimum size, widths that are not multiples of 4 / 32 / 64 / 128 (byte-wise load paths, partial tiles, 1-word resize windows)"""
+    import efb200, efo
+    torch = torch_cuda
+    img = oracle.synth_frame(util.SEED + 51, w * 1000 + h, w, h)
+    for dtype_name in ("BAD_256", "HASH_SIFT_256"):
+        ef = make_ef(nfeatures=500, nlevels=4, dtype=getattr(efb200, dtype_name), max_width=w, max_height=h)
+        kp, desc = ef.detectAndComputeAsync(torch.from_numpy(img).cuda())
+        ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(nfeatures=500, nlevels=4, desc_type=getattr(efo, dtype_name)))
+        g, o = ef.convert(kp), util.oracle_to_struct(ok)
+        util.assert_keypoints_equal(g, o)
+        if len(g):
+            _, go = util.canon_keypoints(g)
+            _, oo = util.canon_keypoints(o)
+            assert np.array_equal(desc.cpu().numpy()[go], od[oo])
+
+
+def test_unaligned_caller_image(torch_cuda, oracle):
+    """level 0 is the caller's buffer: odd base address and odd pitch (a column slice of a larger tensor)"""
+    import efb200, efo
+    torch = torch_cuda
+    w, h = 517, 389
+    img = oracle.synth_frame(util.SEED + 52, 0, w, h)
+    big = torch.zeros((h, w + 6), dtype=torch.uint8, device="cuda")
+    big[:, 3:3 + w] = torch.from_numpy(img).cuda()
+    view = big[:, 3:3 + w]                      # data_ptr % 4 == 3, stride(0) = w + 6 = 523 (odd)
+    assert view.data_ptr() % 4 != 0 and view.stride(0) % 4 != 0
+    for dtype_name in ("BAD_512", "HASH_SIFT_512"):
+        ef = make_ef(nfeatures=1500, dtype=getattr(efb200, dtype_name), max_width=w, max_height=h)
+        kp, desc = ef.detectAndComputeAsync(view)
+        ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(nfeatures=1500, desc_type=getattr(efo, dtype_name)))
+        g, o = ef.convert(kp), util.oracle_to_struct(ok)
+        util.assert_keypoints_equal(g, o)
+        _, go = util.canon_keypoints(g)
+        _, oo = util.canon_keypoints(o)
+        assert np.array_equal(desc.cpu().numpy()[go], od[oo])
+
+
+@pytest.mark.parametrize("radius", [1, 2, 3, 4, 7, 9, 10, 11, 31, 64])
+def test_nms_radius_sweep(torch_cuda, oracle, radius):
+    """block edge 0 (no suppression), 2, 4 and 8 of the block-maximum NMS, and the widest neighbourhood (r = 64)"""
+    import efb200, efo
+    torch = torch_cuda
+    w, h = 640, 360
+    img = oracle.synth_frame(util.SEED + 53, radius, w, h)
+    p = dict(nfeatures=4000, scale_factor=1.2, nlevels=5, first_level=0, fast_threshold=25, nonmax_radius=radius)
+    ef = make_ef(nfeatures=p["nfeatures"], nlevels=p["nlevels"], fastThreshold=p["fast_threshold"], nonmaxRadius=radius,
+                 dtype=efb200.BAD_256, max_width=w, max_height=h)
+    g = ef.detect(torch.from_numpy(img).cuda())
+    ok, _ = oracle.detect(img, oracle.make_params(desc_type=efo.BAD_256, **p))
+    util.assert_keypoints_equal(g, util.oracle_to_struct(ok))
+
+
+@pytest.mark.parametrize("kw", [dict(scale_factor=1.1, nlevels=12), dict(scale_factor=2.0, nlevels=4), dict(scale_factor=1.3, nlevels=1),
+                                dict(fast_threshold=0, nfeatures=3000), dict(fast_threshold=255), dict(nfeatures=1), dict(nfeatures=100000)])
+def test_parameter_extremes(torch_cuda, oracle, kw):
+    import efb200, efo
+    torch = torch_cuda
+    w, h = 512, 384
+    img = oracle.synth_frame(util.SEED + 54, 0, w, h)
+    p = dict(nfeatures=2000, scale_factor=1.2, nlevels=8, first_level=0, fast_threshold=20, nonmax_radius=15)
+    p.update(kw)
+    ef = make_ef(nfeatures=p["nfeatures"], scaleFactor=p["scale_factor"], nlevels=p["nlevels"], fastThreshold=p["fast_threshold"],
+                 dtype=efb200.HASH_SIFT_256, max_width=w, max_height=h)
+    kp, desc = ef.detectAndComputeAsync(torch.from_numpy(img).cuda())
+    ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(desc_type=efo.HASH_SIFT_256, **p))
+    g, o = ef.convert(kp), util.oracle_to_struct(ok)
+    util.assert_keypoints_equal(g, o)
+    if len(g):
+        _, go = util.canon_keypoints(g)
+        _, oo = util.canon_keypoints(o)
+        assert np.array_equal(desc.cpu().numpy()[go], od[oo])
+
+
+@pytest.mark.parametrize("value", [0, 255, "gradient", "checker"])
+def test_degenerate_images(torch_cuda, oracle, value):
+    """constant images (no corner), a smooth ramp (ties everywhere) and a 1-px checkerboard (every interior pixel is a corner,
+    all Harris responses of a row equal: exercises the tie rules of the block-maximum NMS and of the top-K select)"""
+    import efb200, efo
+    torch = torch_cuda
+    w, h = 320, 240
+    if value == "gradient":
+        img = ((np.arange(w)[None, :] + 2 * np.arange(h)[:, None]) % 256).astype(np.uint8)
+    elif value == "checker":
+        img = (((np.arange(w)[None, :] + np.arange(h)[:, None]) % 2) * 255).astype(np.uint8)
+    else:
+        img = np.full((h, w), value, np.uint8)
+    img = np.ascontiguousarray(img)
+    ef = make_ef(nfeatures=1000, nlevels=3, dtype=efb200.BAD_256, max_width=w, max_height=h)
+    kp, desc = ef.detectAndComputeAsync(torch.from_numpy(img).cuda())
+    ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(nfeatures=1000, nlevels=3, desc_type=efo.BAD_256))
+    g, o = ef.convert(kp), util.oracle_to_struct(ok)
+    util.assert_keypoints_equal(g, o)
+    if len(g):
+        _, go = util.canon_keypoints(g)
+        _, oo = util.canon_keypoints(o)
+        assert np.array_equal(desc.cpu().numpy()[go], od[oo])

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 SEL=""
 if [ -n "$QUICK" ]; then SEL="-k test_stages_match_oracle or (test_detect_and_compute_matches_oracle and 800) or test_detect_only_and_params or test_host_api_and_batch"; fi
-echo "### pytest"; timeout 1500 python -m pytest tests -m gpu -q --tb=short -x -p no:cacheprovider --durations=4 ${SEL:+"$SEL"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/pytest_gpu.log
+echo "### pytest"; timeout 1500 python -m pytest tests -m gpu -q --tb=short ${NOX:--x} -p no:cacheprovider --durations=4 ${SEL:+"$SEL"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/pytest_gpu.log
 echo "### bench"; timeout 900 python bench.py --steps 5 --warmup 3 --batch 8 ${BENCH_ARGS} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; python - <<'PY'
 import json
 try:
