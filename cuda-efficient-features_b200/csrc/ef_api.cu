@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -387,6 +388,7 @@ int allocate(ef_handle* h)
     EF_CUDA(h, cudaMallocHost((void**)&h->h_counts_pinned, sizeof(int) * (p.max_batch + EF_MAX_LEVELS * 4)));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    if (const char* e = std::getenv("EF_B200_HOST_CHUNK")) h->host_chunk = std::max(1, std::atoi(e)); // frames per pipeline chunk of the host API
     h->ev_in.resize(p.max_batch); h->ev_cnt.resize(p.max_batch);
     for (int i = 0; i < p.max_batch; i++) {
         EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));

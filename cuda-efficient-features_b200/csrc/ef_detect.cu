@@ -514,6 +514,9 @@ __device__ __forceinline__ bool ef_nms_scan_block(const float* __restrict__ resp
     return hit;
 }
 
+// TB, TK: block edge and block reach of the disc as compile-time constants (8, 2 for the default radius 15: no runtime divisions,
+// unrolled neighbour walk); TB = 0: taken from the parameter block (any radius).
+template <int TB, int TK>
 __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ unsigned s_mask[EF_NMS_RT * EF_TILE];
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     const int x0 = tx0 * EF_TILE, y0 = ty * EF_TILE;
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
 
-    const int b = p.nms_block;
+    const int b = TB ? TB : p.nms_block;
     if (tid < EF_NMS_RT * EF_TILE) s_mask[tid] = 0;
     if (b == 0) {
         // r^2 <= 1: the disc holds only the pixel itself, every corner survives
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     } else {
         const EfBlockMax* __restrict__ bmap = reinterpret_cast<const EfBlockMax*>(ef_ws(p, frame, L.blk_off));
         const int lb = 31 - __clz(b), nb = EF_TILE >> lb, lrx = 2 + 5 - lb;   // strip = (4 nb) x nb blocks, 4 nb = 1 << lrx
-        const int K = p.nms_K, r2 = p.nms_r2;
+        const int K = TB ? TK : p.nms_K, r2 = p.nms_r2;
         const int side_x = (EF_NMS_RT * nb) + 2 * K, side_y = nb + 2 * K;
         const int sbx0 = (x0 >> lb) - K, sby0 = (y0 >> lb) - K;                // block coordinates of s_blk[0]
         for (int i = tid; i < side_x * side_y; i += 256) {
@@ -644,7 +647,8 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
 void ef_launch_nms(const EfPipe& p, cudaStream_t s)
 {
     if (p.total_strips <= 0) return;
-    ef_nms_kernel<<<dim3(p.total_strips, p.nframes), 256, 0, s>>>(p);
+    if (p.nms_block == 8 && p.nms_K == 2) ef_nms_kernel<8, 2><<<dim3(p.total_strips, p.nframes), 256, 0, s>>>(p);
+    else ef_nms_kernel<0, 0><<<dim3(p.total_strips, p.nframes), 256, 0, s>>>(p);
     EF_COUNT_LAUNCH(1);
 }
 

@@ -1,10 +1,14 @@
 #!/bin/bash
-# ncu launch list + full capture of the hot kernels (1 GPU).  Outputs -> gpurun_out/
+# Evidence run for profiles/: ncu launch list (gpu__time_duration) + full capture of every kernel of one step (1 GPU).
+# Outputs -> gpurun_out/; summarise here with tools/ncu_summary.py (see profiles/README.md).
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline"
-echo "### launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 15 -c 15 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/launches.out 2>&1
-echo "exit $?"; tail -3 gpurun_out/launches.out
-echo "### full capture"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ef_hashsift_pipe|ef_nms|ef_score|ef_hashsift_project|ef_resize|ef_blur|ef_bad_pipe" -s 12 -c 12 -o gpurun_out/prof_full -f $B > gpurun_out/prof_full.out 2>&1
-echo "exit $?"; tail -3 gpurun_out/prof_full.out; ls -la gpurun_out
+echo "### launch list (HashSIFT-512)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 15 -c 15 --csv --log-file gpurun_out/launches_hs.csv $B > gpurun_out/launches_hs.out 2>&1; echo "exit $?"
+echo "### launch list (BAD-512)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 14 -c 14 --csv --log-file gpurun_out/launches_bad.csv $B --desc BAD_512 > gpurun_out/launches_bad.out 2>&1; echo "exit $?"
+echo "### full capture (HashSIFT-512 step)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"ef_" -s 15 -c 15 -o gpurun_out/prof_all -f $B > gpurun_out/prof_all.out 2>&1; echo "exit $?"
+echo "### full capture (BAD-512 describe)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ef_bad_pipe" -s 1 -c 1 -o gpurun_out/prof_bad -f $B --desc BAD_512 > gpurun_out/prof_bad.out 2>&1; echo "exit $?"
+ls -la gpurun_out | tail -12
