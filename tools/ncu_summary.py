@@ -41,6 +41,8 @@ def main():
     traffic = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0]
+        if name.startswith("void "):
+            name = name[5:]
         cells = [name, r[idx["Grid Size"]]]
         for key, _ in COLS:
             if key in idx:
