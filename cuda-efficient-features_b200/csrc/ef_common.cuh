@@ -104,7 +104,7 @@ __device__ __forceinline__ unsigned ef_float_key(float f)
 
 // every kernel launch of the library is counted (bench.py reports it as gpu_launches)
 extern unsigned long long g_ef_launches;
-#define EF_COUNT_LAUNCH(n) (g_ef_launches += (unsigned long long)(n))
+#define EF_COUNT_LAUNCH(n) ((void)__atomic_fetch_add(&g_ef_launches, (unsigned long long)(n), __ATOMIC_RELAXED)) // host threads of ef_mg_*
 
 // ---- launchers (host) ----------------------------------------------------------------------------
 void ef_launch_pyramid(const EfPipe& p, cudaStream_t s);

@@ -319,10 +319,13 @@ void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
 {
     if (p.total_kpt_blocks <= 0) return;
     const size_t smem = (size_t)EF_DESC_WARPS * (EF_BW_ROWS + 1) * EF_BW_WORDS * sizeof(unsigned);
-    static bool configured = false;
-    if (!configured) {
+    // function attributes are per device (ef_mg_* drives several devices from one process)
+    static unsigned long long configured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((__atomic_load_n(&configured, __ATOMIC_RELAXED) >> (dev & 63)) & 1ull)) {
         cudaFuncSetAttribute(ef_bad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
     }
     ef_bad_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t);
     EF_COUNT_LAUNCH(1);

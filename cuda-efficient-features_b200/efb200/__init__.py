@@ -34,6 +34,8 @@ EXPORTS = [
     "ef_detect_and_compute_host", "ef_detect_and_compute_host_batch", "ef_debug_level_view",
     "ef_debug_level_counts", "ef_debug_keep_projection", "ef_debug_hashsift_views", "ef_debug_copy_to_host",
     "ef_stage_timing_enable", "ef_stage_times", "ef_kernel_launch_count",
+    "ef_mg_create", "ef_mg_destroy", "ef_mg_device_count", "ef_mg_shard_range", "ef_mg_detect_and_compute_host_batch",
+    "ef_mg_last_error_string",
 ]
 STAGE_NAMES = ["pyramid", "score", "nms", "compact", "select", "angle_pack", "blur", "describe", "project"]
 
@@ -94,6 +96,15 @@ def load_library() -> C.CDLL:
     L.ef_stage_timing_enable.argtypes = [vp, i32]
     L.ef_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     L.ef_kernel_launch_count.restype = C.c_ulonglong
+    L.ef_mg_create.argtypes = [C.POINTER(ef_params), C.POINTER(i32), i32, C.POINTER(vp)]
+    L.ef_mg_destroy.argtypes = [vp]
+    L.ef_mg_destroy.restype = None
+    L.ef_mg_device_count.argtypes = [vp]
+    L.ef_mg_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.ef_mg_shard_range.restype = None
+    L.ef_mg_detect_and_compute_host_batch.argtypes = [vp, i32, vp, sz, sz, i32, i32, vp, vp, C.POINTER(i32)]
+    L.ef_mg_last_error_string.argtypes = [vp]
+    L.ef_mg_last_error_string.restype = C.c_char_p
     _lib = L
     return L
 
@@ -431,6 +442,55 @@ class EfficientFeatures:
         sift = self._copy_2d(a.value, 128, 128, n, 1, np.uint8)
         proj = self._copy_2d(b.value, nbits * 4, nbits, n, 4, np.float32) if b.value else None
         return sift, proj
+
+
+class MultiGpuEfficientFeatures:
+    """Single-process multi-GPU driver (ef_mg_*): one handle, host thread and stream per device, frames sharded in contiguous
+    blocks, no cross-GPU exchange on the data path.  Host (numpy / pinned torch) buffers in and out."""
+
+    def __init__(self, devices=None, nfeatures=5000, scaleFactor=1.2, nlevels=8, firstLevel=0, fastThreshold=20, nonmaxRadius=15,
+                 dtype=HASH_SIFT_256, max_width=3840, max_height=2160, max_batch=4):
+        L = load_library()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise EfError("no CUDA device: the detectAndCompute path exists only as sm_100a kernels (no CPU fallback)")
+        devices = list(range(torch.cuda.device_count())) if devices is None else list(devices)
+        p = ef_params()
+        L.ef_default_params(C.byref(p))
+        p.nfeatures, p.scale_factor, p.nlevels, p.first_level = nfeatures, scaleFactor, nlevels, firstLevel
+        p.fast_threshold, p.nonmax_radius, p.desc_type = fastThreshold, nonmaxRadius, dtype
+        p.max_width, p.max_height, p.max_batch = max_width, max_height, max_batch
+        self.L, self.nfeatures, self.desc_bytes, self.devices = L, nfeatures, _desc_bytes(dtype), devices
+        self.h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = L.ef_mg_create(C.byref(p), arr, len(devices), C.byref(self.h))
+        if rc != 0:
+            raise EfError(f"ef_mg_create failed with status {rc}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.ef_mg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detectAndComputeHost(self, frames: np.ndarray, want_descriptors=True):
+        """frames: F x H x W uint8 (host).  Returns (list of 5 x N_f keypoint matrices, list of N_f x B descriptors)."""
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.strides[2] != 1:
+            raise EfError("frames must be F x H x W uint8")
+        F, H, W = frames.shape
+        kp = np.zeros((F, ROWS_COUNT, self.nfeatures), np.float32)
+        desc = np.zeros((F, self.nfeatures, self.desc_bytes), np.uint8) if want_descriptors else None
+        counts = (C.c_int * F)()
+        rc = self.L.ef_mg_detect_and_compute_host_batch(self.h, F, frames.ctypes.data, frames.strides[0], frames.strides[1], W, H,
+                                                        kp.ctypes.data, desc.ctypes.data if want_descriptors else None, counts)
+        if rc != 0:
+            raise EfError(f"status {rc}: {self.L.ef_mg_last_error_string(self.h).decode()}")
+        return [kp[f][:, :counts[f]] for f in range(F)], [desc[f][:counts[f]] if want_descriptors else None for f in range(F)]
 
 
 class _Describer:

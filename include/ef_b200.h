@@ -124,6 +124,19 @@ int ef_detect_and_compute_host(ef_handle* h, const uint8_t* h_img, size_t pitch,
 int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h_imgs, size_t img_stride, size_t pitch,
                                      int width, int height, float* h_kpts5, uint8_t* h_desc, int* h_counts, void* stream);
 
+/* ---- single-process multi-GPU driver (new): frames are independent, a batch is cut into contiguous per-device
+ * blocks and every device runs the single-GPU pipeline on its block from its own host thread and stream; no cross-GPU
+ * exchange on the data path.  params->device is ignored; devices == NULL means ordinals 0 .. ndev-1; params->max_batch is the
+ * sub-batch size per device.  Host buffers as in ef_detect_and_compute_host_batch (nframes may exceed max_batch). */
+typedef struct ef_mg_handle ef_mg_handle;
+int ef_mg_create(const ef_params* params, const int* devices, int ndev, ef_mg_handle** out);
+void ef_mg_destroy(ef_mg_handle* m);
+int ef_mg_device_count(const ef_mg_handle* m);
+void ef_mg_shard_range(int nframes, int i, int ndev, int* begin, int* end);
+int ef_mg_detect_and_compute_host_batch(ef_mg_handle* m, int nframes, const uint8_t* h_imgs, size_t img_stride, size_t pitch,
+                                        int width, int height, float* h_kpts5, uint8_t* h_desc, int* h_counts);
+const char* ef_mg_last_error_string(const ef_mg_handle* m);
+
 /* ---- introspection for stage-by-stage parity tests (not part of the reference API) ---------- */
 typedef struct ef_level_view {
     int width, height;

@@ -53,3 +53,17 @@ def test_shard_range():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def test_mg_shard_range_matches_python_sharding():
+    """the C driver (ef_mg_shard_range) and the per-process driver (efb200.sharding) cut a batch the same way"""
+    import ctypes as C
+    import efb200
+    from efb200.sharding import shard_range
+    lib = efb200.load_library()
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                b, e = C.c_int(), C.c_int()
+                lib.ef_mg_shard_range(n, r, world, C.byref(b), C.byref(e))
+                assert (b.value, e.value) == shard_range(n, r, world)

@@ -352,3 +352,21 @@ def test_degenerate_images(torch_cuda, oracle, value):
         _, go = util.canon_keypoints(g)
         _, oo = util.canon_keypoints(o)
         assert np.array_equal(desc.cpu().numpy()[go], od[oo])
+
+
+def test_single_process_multi_gpu_driver(torch_cuda, oracle):
+    """ef_mg_*: frames sharded over every visible device (1 on the CI box, 2+ under gpurun --gpus N) from one process;
+    results must equal the single-handle results frame by frame, and the oracle on a sample."""
+    import efb200, efo
+    torch = torch_cuda
+    w, h, F = 640, 480, 7
+    frames = np.stack([oracle.synth_frame(util.SEED + 61, f, w, h) for f in range(F)])
+    mg = efb200.MultiGpuEfficientFeatures(nfeatures=1200, dtype=efb200.BAD_512, max_width=w, max_height=h, max_batch=2)
+    kps, descs = mg.detectAndComputeHost(frames)
+    ef = make_ef(nfeatures=1200, dtype=efb200.BAD_512, max_width=w, max_height=h, max_batch=F)
+    rk, rd = ef._host_call(frames, True)
+    for f in range(F):
+        assert np.array_equal(kps[f].view(np.uint32), rk[f].view(np.uint32)) and np.array_equal(descs[f], rd[f]), f"frame {f}"
+    ok, od, _ = oracle.detect_and_compute(frames[F - 1], oracle.make_params(nfeatures=1200, desc_type=efo.BAD_512))
+    util.assert_keypoints_equal(efb200.EfficientFeatures.convert(kps[F - 1]), util.oracle_to_struct(ok))
+    mg.close()
