@@ -19,6 +19,20 @@
 
 unsigned long long g_ef_launches = 0;
 
+// Tile rows (32-pixel rows of tiles) of one pyramid level owned by band `shard` of `nshards`, and the rows its score stage must
+// cover (owned rows + `halo_tiles` on either side, clipped).  Pure host arithmetic: exported for the host mirrors and tests.
+extern "C" void ef_band_tile_rows(int tiles_y, int shard, int nshards, int halo_tiles, int* own0, int* own_n, int* score0, int* score_n)
+{
+    if (nshards < 1) nshards = 1;
+    if (shard < 0) shard = 0;
+    if (shard >= nshards) shard = nshards - 1;
+    const int a = (int)((long long)tiles_y * shard / nshards), b = (int)((long long)tiles_y * (shard + 1) / nshards);
+    *own0 = a; *own_n = b - a;
+    if (b - a <= 0) { *score0 = a; *score_n = 0; return; }
+    const int sa = std::max(0, a - halo_tiles), sb = std::min(tiles_y, b + halo_tiles);
+    *score0 = sa; *score_n = sb - sa;
+}
+
 namespace {
 
 struct Geometry {
@@ -399,7 +413,8 @@ int allocate(ef_handle* h)
 }
 
 // fill the kernel parameter block for an actual call
-int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
+// shard_i / shard_n: the band of tile rows this GPU owns when one frame is cut over several GPUs (ef_band_*); 0 / 1 = whole frame
+int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i = 0, int shard_n = 1)
 {
     const ef_params& p = h->prm;
     if (w > p.max_width || hh > p.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than max_width x max_height of the handle");
@@ -412,6 +427,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
     const NmsGeom ng = nms_geometry(p.nonmax_radius);
     P.fast_threshold = p.fast_threshold; P.nms_r2 = ng.r2; P.nms_R = ng.R; P.nms_block = ng.block; P.nms_K = ng.K;
     P.nfeatures = p.nfeatures;
+    P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0;
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
     P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
     P.counters = h->d_counters;
@@ -423,6 +439,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
         if (L.w < 1 || L.h < 1) return fail(h, EF_ERR_BAD_ARG, "pyramid level degenerates to zero size; reduce nlevels");
         L.img_pitch = q.img_pitch; L.blur_pitch = q.img_pitch; L.resp_pitch = q.resp_pitch;
         L.tiles_x = ef_div_up(L.w, EF_TILE); L.tiles_y = ef_div_up(L.h, EF_TILE);
+        ef_band_tile_rows(L.tiles_y, shard_i, shard_n, ef_div_up(ng.K * ng.block, EF_TILE), &L.own_ty0, &L.own_rows, &L.score_ty0, &L.score_rows);
         L.blk_w = ng.block ? ef_div_up(L.w, ng.block) : 0; L.blk_h = ng.block ? ef_div_up(L.h, ng.block) : 0;
         L.blur_tiles_x = ef_div_up(L.w, 64);
         L.quota = g.quota[l];
@@ -437,9 +454,9 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P)
         L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks; L.sift_block_start = sblocks;
         L.strips_x = ef_div_up(L.tiles_x, 4); L.strip_start = strips;
         if (l >= p.first_level) {
-            tiles += L.tiles_x * L.tiles_y;
-            strips += L.strips_x * L.tiles_y;
-            bands += L.tiles_y;
+            tiles += L.tiles_x * L.score_rows;
+            strips += L.strips_x * L.own_rows;
+            bands += L.own_rows;
             kblocks += ef_div_up(std::min(L.quota, p.nfeatures), 8);
             sblocks += ef_div_up(std::min(L.quota, p.nfeatures), 4);
             btiles += L.blur_tiles_x * ef_div_up(L.h, 64);
@@ -744,6 +761,90 @@ int ef_detect_and_compute_host(ef_handle* h, const uint8_t* h_img, size_t pitch,
 }
 
 // ---- introspection ------------------------------------------------------------------------------
+size_t ef_band_candidate_bytes(const ef_handle* h)
+{
+    return h ? (size_t)ef_align_up((unsigned long long)EF_BAND_HDR + 8ull * (unsigned long long)h->prm.nfeatures, 16) : 0;
+}
+
+int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
+                         int width, int height, uint8_t* d_cand, void* stream)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (!d_imgs || !d_cand) return fail(h, EF_ERR_BAD_ARG, "null image / candidate pointer");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(h, EF_ERR_BAD_ARG, "shard must be in [0, nshards)");
+    if (pitch < (size_t)width) return fail(h, EF_ERR_BAD_ARG, "pitch smaller than width");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    EfPipe P;
+    int rc = build_pipe(h, nframes, width, height, P, shard, nshards);
+    if (rc != EF_OK) return rc;
+    P.img0 = d_imgs; P.img0_stride = img_stride; P.img0_pitch = (int)pitch;
+    h->last_img0 = d_imgs; h->last_img0_stride = img_stride; h->last_img0_pitch = (int)pitch;
+    EF_CUDA(h, cudaMemset2DAsync(h->d_ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
+    EF_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
+    mark(h, -1, s);
+    ef_launch_pyramid(P, s);      mark(h, EF_STAGE_PYRAMID, s);   // whole pyramid on every GPU: the halo of level s would need level s-1's anyway
+    ef_launch_score(P, s);        mark(h, EF_STAGE_SCORE, s);     // owned tile rows + NMS halo
+    ef_launch_nms(P, s);          mark(h, EF_STAGE_NMS, s);       // owned tile rows
+    ef_launch_compact(P, s);      mark(h, EF_STAGE_COMPACT, s);
+    ef_launch_select(P, s);                                       // local top-quota: superset of this band's share of the global one
+    ef_launch_band_pack(P, d_cand, ef_band_candidate_bytes(h), s);
+    mark(h, EF_STAGE_SELECT, s);
+    EF_CUDA(h, cudaGetLastError());
+    return EF_OK;
+}
+
+int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_all_cand,
+                         float* d_kpts, size_t kpts_stride, size_t kpts_pitch, uint8_t* d_desc, size_t desc_stride, size_t desc_pitch,
+                         int* d_counts, void* stream)
+{
+    if (!h) return EF_ERR_BAD_ARG;
+    if (!d_all_cand || !d_kpts || !d_counts) return fail(h, EF_ERR_BAD_ARG, "null candidate / keypoint / count pointer");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(h, EF_ERR_BAD_ARG, "shard must be in [0, nshards)");
+    if (h->last_w == 0 || nframes != h->last_nframes || !h->last_img0) return fail(h, EF_ERR_BAD_ARG, "ef_band_finish_async must follow ef_band_detect_async on the same handle");
+    if (kpts_pitch < (size_t)h->prm.nfeatures * 4 || (kpts_pitch & 3)) return fail(h, EF_ERR_BAD_ARG, "kpts_pitch must be >= 4*nfeatures and a multiple of 4");
+    const int db = desc_bytes_of(h->prm.desc_type);
+    if (d_desc && desc_pitch < (size_t)db) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    EfPipe P;
+    int rc = build_pipe(h, nframes, h->last_w, h->last_h, P, shard, nshards);
+    if (rc != EF_OK) return rc;
+    P.img0 = h->last_img0; P.img0_stride = h->last_img0_stride; P.img0_pitch = h->last_img0_pitch;
+    P.kpts = d_kpts; P.kpts_stride = kpts_stride; P.kpts_pitch = (int)kpts_pitch;
+    P.desc = d_desc; P.desc_stride = desc_stride; P.desc_pitch = (int)desc_pitch;
+    P.counts = d_counts;
+    P.select_from_counters = 1;
+    mark(h, -1, s);
+    ef_launch_band_merge(P, d_all_cand, ef_band_candidate_bytes(h), nshards, s);
+    ef_launch_select(P, s);       mark(h, EF_STAGE_SELECT, s);    // global top-quota over the concatenated bands (raster order)
+    ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);// every GPU writes the full keypoint matrix (identical everywhere)
+    if (d_desc) {
+        ef_launch_blur(P, s);     mark(h, EF_STAGE_BLUR, s);
+        // descriptor CTAs are dealt round-robin; rows of other GPUs stay zero: MAX all-reduce assembles the matrix
+        P.shard_i = shard; P.shard_n = nshards;
+        for (int f = 0; f < nframes; f++)
+            EF_CUDA(h, cudaMemset2DAsync(d_desc + f * desc_stride, desc_pitch, 0, (size_t)db, (size_t)h->prm.nfeatures, s));
+        const int v = (db == 32) ? 0 : 1;
+        if (is_bad(P.desc_type)) {
+            EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
+            ef_launch_bad_pipe(P, t, s);
+            mark(h, EF_STAGE_DESCRIBE, s);
+        } else {
+            EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
+            ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
+            mark(h, EF_STAGE_DESCRIBE, s);
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+            ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, db * 8,
+                                             P.desc, (size_t)P.desc_stride, P.desc_pitch, nullptr, s);
+            if (nshards > 1) ef_launch_band_mask_rows(P, true, s);
+            mark(h, EF_STAGE_PROJECT, s);
+        }
+    }
+    EF_CUDA(h, cudaGetLastError());
+    return EF_OK;
+}
+
 int ef_debug_level_view(const ef_handle* h, int frame, int level, ef_level_view* out)
 {
     if (!h || !out || level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->prm.max_batch || h->last_w == 0) return EF_ERR_BAD_ARG;

@@ -33,6 +33,10 @@ struct EfLevel {
     int blur_pitch;     // bytes
     int resp_pitch;     // floats
     int tiles_x, tiles_y;
+    // tile rows this call works on (whole level unless the frame is cut into bands over several GPUs, ef_band_*):
+    // the score stage covers rows [score_ty0, score_ty0 + score_rows) = the owned rows plus the NMS halo,
+    // NMS / compaction the owned rows [own_ty0, own_ty0 + own_rows)
+    int score_ty0, score_rows, own_ty0, own_rows;
     int blk_w, blk_h;   // dimensions of the NMS block-maximum map (ceil(w / nms_block), ceil(h / nms_block))
     int tile_start;     // first tile index of this level in the all-level tile table
     int strips_x, strip_start; // NMS strips of 4 tiles per tile row; first strip index of this level
@@ -56,6 +60,8 @@ struct EfPipe {
     int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks, total_sift_blocks, total_strips;
     int nfeatures;              // output capacity (columns)
     int desc_type, desc_bytes;
+    int shard_i, shard_n;       // descriptor CTAs are dealt round-robin to shard_n GPUs (ef_band_finish_async); 0, 1 otherwise
+    int select_from_counters;   // select stage: candidate count comes from counters[].overflow (merged band candidates), not from rowcnt
     // caller buffers (frame f at base + f*stride)
     const uint8_t* img0; unsigned long long img0_stride; int img0_pitch;
     float* kpts; unsigned long long kpts_stride; int kpts_pitch;      // bytes
@@ -114,6 +120,11 @@ void ef_launch_compact(const EfPipe& p, cudaStream_t s);
 void ef_launch_select(const EfPipe& p, cudaStream_t s);
 void ef_launch_angle_pack(const EfPipe& p, cudaStream_t s);
 void ef_launch_blur(const EfPipe& p, cudaStream_t s);
+// band-sharded single frame (ef_band_*): packed per-band candidates, merge of all bands, ownership mask of descriptor rows
+#define EF_BAND_HDR 256
+void ef_launch_band_pack(const EfPipe& p, uint8_t* cand, unsigned long long cand_stride, cudaStream_t s);
+void ef_launch_band_merge(const EfPipe& p, const uint8_t* all, unsigned long long cand_stride, int nshards, cudaStream_t s);
+void ef_launch_band_mask_rows(const EfPipe& p, bool hashsift, cudaStream_t s);
 
 // descriptor stage: keypoints either from the per-level selected lists (detectAndCompute) or from a
 // flat caller array (compute-only API)

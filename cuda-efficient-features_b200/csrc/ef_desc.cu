@@ -245,10 +245,12 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int frame = blockIdx.y;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    const int bx = (int)blockIdx.x * p.shard_n + p.shard_i;   // descriptor CTAs dealt round-robin over the GPUs of a band-sharded frame
+    if (bx >= p.total_kpt_blocks) return;
     int level = p.first_level;
-    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].kpt_block_start) level++;
+    while (level + 1 < p.nlevels && bx >= p.lv[level + 1].kpt_block_start) level++;
     const EfLevel& L = p.lv[level];
-    const int i = (blockIdx.x - L.kpt_block_start) * EF_DESC_WARPS + warp;
+    const int i = (bx - L.kpt_block_start) * EF_DESC_WARPS + warp;
     if (i >= ctr[level].selected) return;
     int offset = 0;
     for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
@@ -327,7 +329,7 @@ void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
         cudaFuncSetAttribute(ef_bad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
     }
-    ef_bad_pipe_kernel<<<dim3(p.total_kpt_blocks, p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t);
+    ef_bad_pipe_kernel<<<dim3(ef_div_up(p.total_kpt_blocks, p.shard_n), p.nframes), EF_DESC_WARPS * 32, smem, s>>>(p, t);
     EF_COUNT_LAUNCH(1);
 }
 

@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.tile_start;
-    const int ty = t / L.tiles_x;
-    const int x0 = (t - ty * L.tiles_x) * EF_TILE, y0 = ty * EF_TILE;
+    const int tyl = t / L.tiles_x, ty = tyl + L.score_ty0;
+    const int x0 = (t - tyl * L.tiles_x) * EF_TILE, y0 = ty * EF_TILE;
 
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ E
             const float tt = tr * (-0.04f);
             s_resp[cy][cx] = fmaf(tr, tt, det);
         }
-        if (tid == 0) atomicAdd(&p.counters[frame * EF_MAX_LEVELS + level].corners, n);
+        if (tid == 0 && (unsigned)(ty - L.own_ty0) < (unsigned)L.own_rows) atomicAdd(&p.counters[frame * EF_MAX_LEVELS + level].corners, n);
     }
     __syncthreads();
 
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfP
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::strip_start);
     const EfLevel& L = p.lv[level];
     const int s = blockIdx.x - L.strip_start;
-    const int ty = s / L.strips_x, tx0 = (s - ty * L.strips_x) * EF_NMS_RT;
+    const int tyl = s / L.strips_x, ty = tyl + L.own_ty0, tx0 = (s - tyl * L.strips_x) * EF_NMS_RT;
     const int ntx = min(EF_NMS_RT, L.tiles_x - tx0);
     const int x0 = tx0 * EF_TILE, y0 = ty * EF_TILE;
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(1024) ef_compact_kernel(const __grid_constant_
     const int frame = blockIdx.y;
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::band_start);
     const EfLevel& L = p.lv[level];
-    const int band = blockIdx.x - L.band_start;
+    const int band = blockIdx.x - L.band_start + L.own_ty0;
     const int y0 = band * EF_TILE;
     const int* __restrict__ rowcnt = reinterpret_cast<const int*>(ef_ws(p, frame, L.rowcnt_off));
 
@@ -783,16 +783,26 @@ __global__ void __launch_bounds__(1024) ef_select_kernel(const __grid_constant__
     EfSelected* sel = reinterpret_cast<EfSelected*>(ef_ws(p, frame, L.sel_off));
     EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS + level];
 
-    int partial = 0;
-    for (int i = tid; i < L.h; i += 1024) partial += rowcnt[i];
+    int ntotal = 0, ncand = 0;
+    if (p.select_from_counters) {
+        // second pass of the band-sharded path: the list holds the merged per-band candidates (ef_band_merge_kernel left their
+        // number in .overflow and the true survivor count of the level in .survivors)
+        if (tid == 0) { s_warp[0] = ctr->survivors; s_warp[1] = ctr->overflow; }
+        __syncthreads();
+        ntotal = s_warp[0]; ncand = s_warp[1];
+        __syncthreads();
+    } else {
+        int partial = 0;
+        for (int i = tid; i < L.h; i += 1024) partial += rowcnt[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
-    if (lane == 0) s_warp[warp] = partial;
-    __syncthreads();
-    int ntotal = 0;
-    for (int i = 0; i < 32; i++) ntotal += s_warp[i];
-    __syncthreads();
-    const int n = min(ntotal, L.surv_cap);
+        for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
+        if (lane == 0) s_warp[warp] = partial;
+        __syncthreads();
+        for (int i = 0; i < 32; i++) ntotal += s_warp[i];
+        __syncthreads();
+        ncand = ntotal;
+    }
+    const int n = min(ncand, L.surv_cap);
     const int quota = L.quota;
 
     if (n <= quota) {
@@ -801,7 +811,7 @@ __global__ void __launch_bounds__(1024) ef_select_kernel(const __grid_constant__
             EfSelected o; o.x = sv.x; o.y = sv.y; o.resp = sv.resp; o.angle = 0.f; o.pad = 0;
             sel[i] = o;
         }
-        if (tid == 0) { ctr->survivors = ntotal; ctr->selected = n; ctr->overflow = ntotal > L.surv_cap; }
+        if (tid == 0) { ctr->survivors = ntotal; ctr->selected = n; ctr->overflow = ncand > L.surv_cap; }
         return;
     }
 
@@ -852,7 +862,7 @@ __global__ void __launch_bounds__(1024) ef_select_kernel(const __grid_constant__
         run_eq += tot_eq;
         run_sel += tot_sel;
     }
-    if (tid == 0) { ctr->survivors = ntotal; ctr->selected = min(run_sel, quota); ctr->overflow = ntotal > L.surv_cap; }
+    if (tid == 0) { ctr->survivors = ntotal; ctr->selected = min(run_sel, quota); ctr->overflow = ncand > L.surv_cap; }
 }
 
 void ef_launch_select(const EfPipe& p, cudaStream_t s)
@@ -1057,5 +1067,104 @@ void ef_launch_blur(const EfPipe& p, cudaStream_t s)
 {
     if (p.total_blur_tiles <= 0) return;
     ef_blur_kernel<<<dim3(p.total_blur_tiles, p.nframes), 256, 0, s>>>(p);
+    EF_COUNT_LAUNCH(1);
+}
+
+// =================================================================================================
+// One oversized frame over several GPUs (north_star "image tiles with halo"): every GPU holds the whole image
+// and builds the whole pyramid (bandwidth-trivial), but scores / suppresses / compacts only its band of tile rows (plus the
+// NMS halo for the score stage).  The per-level top-quota needs all bands: each GPU keeps its LOCAL top-quota (a superset of
+// its share of the global one), the packed candidate lists are all-gathered by the caller (NCCL over NVLink, <= 8 B x
+// nfeatures per GPU), and every GPU re-selects over the concatenation -- bands are ordered by rows, so the concatenation is
+// in raster order and the result is the single-GPU selection bit for bit.
+//
+// candidate buffer of one frame: int header[3][EF_MAX_LEVELS] = {selected, survivors, corners} of the band, padded to
+// EF_BAND_HDR bytes; then for level l the EfSurvivor entries at EF_BAND_HDR + 8 * sum(quota[l'] : l' < l).
+// =================================================================================================
+__global__ void __launch_bounds__(256) ef_band_pack_kernel(const __grid_constant__ EfPipe p, uint8_t* __restrict__ cand, unsigned long long cand_stride)
+{
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const EfLevel& L = p.lv[level];
+    const EfLevelCounters c = p.counters[frame * EF_MAX_LEVELS + level];
+    uint8_t* out = cand + (unsigned long long)frame * cand_stride;
+    const int n = level >= p.first_level ? min(c.selected, L.quota) : 0;
+    if (threadIdx.x == 0) {
+        int* hdr = reinterpret_cast<int*>(out);
+        hdr[level] = n;
+        hdr[EF_MAX_LEVELS + level] = level >= p.first_level ? c.survivors : 0;
+        hdr[2 * EF_MAX_LEVELS + level] = level >= p.first_level ? c.corners : 0;
+    }
+    int qoff = 0;
+    for (int l = 0; l < level; l++) qoff += p.lv[l].quota;
+    const EfSelected* __restrict__ sel = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off));
+    EfSurvivor* dst = reinterpret_cast<EfSurvivor*>(out + EF_BAND_HDR) + qoff;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const EfSelected k = sel[i];
+        EfSurvivor sv; sv.x = k.x; sv.y = k.y; sv.resp = k.resp;
+        dst[i] = sv;
+    }
+}
+
+// all: [shard][frame][cand_stride bytes].  Concatenates the bands' candidates of every level into the level's survivor list.
+__global__ void __launch_bounds__(256) ef_band_merge_kernel(const __grid_constant__ EfPipe p, const uint8_t* __restrict__ all, unsigned long long cand_stride, int nshards)
+{
+    const int level = blockIdx.x, frame = blockIdx.y;
+    if (level < p.first_level) return;
+    const EfLevel& L = p.lv[level];
+    int qoff = 0;
+    for (int l = 0; l < level; l++) qoff += p.lv[l].quota;
+    EfSurvivor* surv = reinterpret_cast<EfSurvivor*>(ef_ws(p, frame, L.surv_off));
+    int base = 0, nsurv = 0, ncorn = 0;
+    for (int g = 0; g < nshards; g++) {
+        const uint8_t* in = all + ((unsigned long long)g * p.nframes + frame) * cand_stride;
+        const int* hdr = reinterpret_cast<const int*>(in);
+        const int n = min(max(hdr[level], 0), L.quota);
+        nsurv += hdr[EF_MAX_LEVELS + level];
+        ncorn += hdr[2 * EF_MAX_LEVELS + level];
+        const EfSurvivor* __restrict__ src = reinterpret_cast<const EfSurvivor*>(in + EF_BAND_HDR) + qoff;
+        for (int i = threadIdx.x; i < n; i += 256)
+            if (base + i < L.surv_cap) surv[base + i] = src[i];
+        base += n;
+    }
+    if (threadIdx.x == 0) {
+        EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS + level];
+        ctr->corners = ncorn; ctr->survivors = nsurv; ctr->overflow = base; ctr->selected = 0;
+    }
+}
+
+// zero the descriptor rows whose HashSIFT feature CTA belongs to another GPU (their SIFT vectors were not computed here),
+// so that an element-wise MAX all-reduce of the descriptor matrices assembles the frame's descriptors
+__global__ void __launch_bounds__(256) ef_band_mask_rows_kernel(const __grid_constant__ EfPipe p, int hashsift)
+{
+    const int frame = blockIdx.y;
+    const int chunks = p.desc_bytes / 16;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int row = idx / chunks, ch = idx - row * chunks;
+    if (row >= min(p.counts[frame], p.nfeatures)) return;
+    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    int level = p.first_level, offset = 0;
+    while (level + 1 < p.nlevels && row >= offset + ctr[level].selected) { offset += ctr[level].selected; level++; }
+    const int blk = hashsift ? p.lv[level].sift_block_start + (row - offset) / 4      // EF_SIFT_KP_PER_CTA (ef_hashsift.cu)
+                             : p.lv[level].kpt_block_start + (row - offset) / 8;      // EF_DESC_WARPS (ef_desc.cu)
+    if (blk % p.shard_n == p.shard_i) return;
+    uint8_t* d = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch + 16 * ch;
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+    else for (int i = 0; i < 16; i++) d[i] = 0;
+}
+
+void ef_launch_band_pack(const EfPipe& p, uint8_t* cand, unsigned long long cand_stride, cudaStream_t s)
+{
+    ef_band_pack_kernel<<<dim3(p.nlevels, p.nframes), 256, 0, s>>>(p, cand, cand_stride);
+    EF_COUNT_LAUNCH(1);
+}
+void ef_launch_band_merge(const EfPipe& p, const uint8_t* all, unsigned long long cand_stride, int nshards, cudaStream_t s)
+{
+    ef_band_merge_kernel<<<dim3(p.nlevels, p.nframes), 256, 0, s>>>(p, all, cand_stride, nshards);
+    EF_COUNT_LAUNCH(1);
+}
+void ef_launch_band_mask_rows(const EfPipe& p, bool hashsift, cudaStream_t s)
+{
+    const int threads = p.nfeatures * (p.desc_bytes / 16);
+    ef_band_mask_rows_kernel<<<dim3(ef_div_up(threads, 256), p.nframes), 256, 0, s>>>(p, hashsift ? 1 : 0);
     EF_COUNT_LAUNCH(1);
 }

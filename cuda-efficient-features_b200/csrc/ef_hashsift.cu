@@ -271,13 +271,15 @@ __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_pipe_kernel(co
     const int slot = threadIdx.x >> 4, warp = threadIdx.x >> 5;
     const int frame = blockIdx.y;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    const int bx = (int)blockIdx.x * p.shard_n + p.shard_i;   // CTAs dealt round-robin over the GPUs of a band-sharded frame
+    if (bx >= p.total_sift_blocks) return;
     int level = p.first_level;
-    while (level + 1 < p.nlevels && (int)blockIdx.x >= p.lv[level + 1].sift_block_start) level++;
+    while (level + 1 < p.nlevels && bx >= p.lv[level + 1].sift_block_start) level++;
     const EfLevel& L = p.lv[level];
     const int nsel = ctr[level].selected;
-    const int first = (blockIdx.x - L.sift_block_start) * EF_SIFT_KP_PER_CTA + (slot & ~1);
+    const int first = (bx - L.sift_block_start) * EF_SIFT_KP_PER_CTA + (slot & ~1);
     if (first >= nsel) return;
-    const int i = (blockIdx.x - L.sift_block_start) * EF_SIFT_KP_PER_CTA + slot;
+    const int i = (bx - L.sift_block_start) * EF_SIFT_KP_PER_CTA + slot;
     int offset = 0;
     for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
     const bool valid = i < nsel && offset + i < p.nfeatures;
@@ -293,6 +295,6 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 {
     if (p.total_sift_blocks <= 0) return;
     const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
-    ef_hashsift_pipe_kernel<<<dim3(p.total_sift_blocks, p.nframes), EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128);
+    ef_hashsift_pipe_kernel<<<dim3(ef_div_up(p.total_sift_blocks, p.shard_n), p.nframes), EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128);
     EF_COUNT_LAUNCH(1);
 }

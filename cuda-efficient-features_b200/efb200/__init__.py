@@ -36,6 +36,7 @@ EXPORTS = [
     "ef_stage_timing_enable", "ef_stage_times", "ef_kernel_launch_count",
     "ef_mg_create", "ef_mg_destroy", "ef_mg_device_count", "ef_mg_shard_range", "ef_mg_detect_and_compute_host_batch",
     "ef_mg_last_error_string",
+    "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows",
 ]
 STAGE_NAMES = ["pyramid", "score", "nms", "compact", "select", "angle_pack", "blur", "describe", "project"]
 
@@ -105,6 +106,12 @@ def load_library() -> C.CDLL:
     L.ef_mg_detect_and_compute_host_batch.argtypes = [vp, i32, vp, sz, sz, i32, i32, vp, vp, C.POINTER(i32)]
     L.ef_mg_last_error_string.argtypes = [vp]
     L.ef_mg_last_error_string.restype = C.c_char_p
+    L.ef_band_candidate_bytes.argtypes = [vp]
+    L.ef_band_candidate_bytes.restype = sz
+    L.ef_band_detect_async.argtypes = [vp, i32, i32, i32, vp, sz, sz, i32, i32, vp, vp]
+    L.ef_band_finish_async.argtypes = [vp, i32, i32, i32, vp, vp, sz, sz, vp, sz, sz, vp, vp]
+    L.ef_band_tile_rows.argtypes = [i32, i32, i32, i32] + [C.POINTER(i32)] * 4
+    L.ef_band_tile_rows.restype = None
     _lib = L
     return L
 
@@ -294,6 +301,45 @@ class EfficientFeatures:
         self._h.check(self._h.L.ef_detect_and_compute_batch_async(
             self._h.h, F, images.data_ptr(), images.stride(0), images.stride(1), W, H,
             kp.data_ptr(), kp.stride(0) * 4, kp.stride(1) * 4,
+            desc.data_ptr() if desc is not None else None, desc.stride(0) if desc is not None else 0,
+            desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream)))
+        return kp, desc, counts
+
+    # ---- one oversized frame over several GPUs (ef_band_*; see efb200/tiling.py for the collective plumbing) ----
+    def bandCandidateBytes(self) -> int:
+        return int(self._h.L.ef_band_candidate_bytes(self._h.h))
+
+    def bandDetect(self, images, shard: int, nshards: int, stream=None):
+        """Phase 1 on band `shard` of `nshards`: pyramid, FAST/Harris + radius NMS on the band, local top-quota.
+        images: F x H x W uint8 CUDA tensor (the WHOLE frame on every GPU).  Returns the packed candidates
+        (F x bandCandidateBytes() uint8 CUDA tensor) to be all-gathered in shard order."""
+        torch = _torch()
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8 and images.dim() == 3 and images.stride(2) == 1):
+            raise EfError("images must be an F x H x W uint8 CUDA tensor")
+        F, H, W = images.shape
+        cand = torch.empty((F, self.bandCandidateBytes()), dtype=torch.uint8, device=images.device)
+        self._h.check(self._h.L.ef_band_detect_async(self._h.h, shard, nshards, F, images.data_ptr(), images.stride(0), images.stride(1),
+                                                     W, H, cand.data_ptr(), _stream_ptr(stream)))
+        self._band_images = images  # level 0 of the pyramid aliases the caller's image until bandFinish
+        return cand
+
+    def bandFinish(self, all_cand, shard: int, nshards: int, stream=None, want_descriptors=True, out=None):
+        """Phase 2: all_cand = nshards x F x bandCandidateBytes() (all-gathered).  Returns (F x 5 x nfeatures keypoints --
+        complete and identical on every GPU --, F x nfeatures x B descriptors with only this GPU's rows non-zero, F counts)."""
+        torch = _torch()
+        if not (isinstance(all_cand, torch.Tensor) and all_cand.is_cuda and all_cand.dtype == torch.uint8 and all_cand.is_contiguous()
+                and all_cand.dim() == 3 and all_cand.shape[0] == nshards and all_cand.shape[2] == self.bandCandidateBytes()):
+            raise EfError("all_cand must be a contiguous nshards x F x bandCandidateBytes() uint8 CUDA tensor")
+        F = all_cand.shape[1]
+        nf = int(self._h.get(PARAM_MAX_FEATURES))
+        if out is None:
+            kp = torch.empty((F, ROWS_COUNT, nf), dtype=torch.float32, device=all_cand.device)
+            desc = torch.empty((F, nf, self.descriptorSize()), dtype=torch.uint8, device=all_cand.device) if want_descriptors else None
+            counts = torch.zeros(F, dtype=torch.int32, device=all_cand.device)
+        else:
+            kp, desc, counts = out
+        self._h.check(self._h.L.ef_band_finish_async(
+            self._h.h, shard, nshards, F, all_cand.data_ptr(), kp.data_ptr(), kp.stride(0) * 4, kp.stride(1) * 4,
             desc.data_ptr() if desc is not None else None, desc.stride(0) if desc is not None else 0,
             desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream)))
         return kp, desc, counts

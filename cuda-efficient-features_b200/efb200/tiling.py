@@ -1,0 +1,59 @@
+"""One oversized frame over several GPUs: horizontal bands with halo (SURVEY 8e "one oversized frame").
+
+Every rank holds the whole image (rank `src` broadcasts it over NCCL/NVLink -- the only image movement), builds the whole
+pyramid, and runs FAST/Harris + radius NMS + compaction on its band of every level.  Two small collectives complete the
+frame: an all-gather of the per-band top-quota candidates (<= 8 B x nfeatures per rank) before the global per-level
+selection, and an element-wise MAX all-reduce of the descriptor matrix (each rank fills only the rows of its share of the
+keypoints, the others are zero).  The result on every rank is bit-identical to the single-GPU result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+
+def band_tile_rows(tiles_y: int, shard: int, nshards: int, halo_tiles: int = 1):
+    """(own0, own_n, score0, score_n): tile rows owned by `shard` and the rows its score stage covers (host arithmetic of
+    ef_band_tile_rows; callable without a GPU)."""
+    from . import load_library
+    L = load_library()
+    v = [C.c_int() for _ in range(4)]
+    L.ef_band_tile_rows(tiles_y, shard, nshards, halo_tiles, *[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def detect_and_compute_tiled(ef, images, group=None, src=None, want_descriptors=True, out=None):
+    """detectAndCompute of F whole frames cut into world_size bands; call on every rank of `group` with an
+    EfficientFeatures created on the rank's GPU.  `images`: F x H x W uint8 CUDA tensor; with `src` given it is
+    broadcast from that rank first (the other ranks pass a buffer of the same shape).  Returns (keypoints F x 5 x nfeatures,
+    descriptors F x nfeatures x B, counts F), complete on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world > 1 and src is not None:
+        dist.broadcast(images, src=src, group=group)
+    cand = ef.bandDetect(images, rank, world)
+    if world > 1:
+        all_cand = torch.empty((world,) + tuple(cand.shape), dtype=torch.uint8, device=cand.device)
+        dist.all_gather_into_tensor(all_cand.view(world * cand.shape[0], cand.shape[1]), cand, group=group)  # rank-major concatenation
+    else:
+        all_cand = cand[None]
+    kp, desc, counts = ef.bandFinish(all_cand, rank, world, want_descriptors=want_descriptors, out=out)
+    if world > 1 and desc is not None:
+        dist.all_reduce(desc, op=dist.ReduceOp.MAX, group=group)
+    return kp, desc, counts
+
+
+def detect_and_compute_tiled_emulated(efs, images, want_descriptors=True):
+    """The same data flow on ONE GPU with len(efs) handles standing in for the ranks (tests, and a reference for the
+    collective plumbing): concatenation replaces the all-gather, an element-wise maximum the all-reduce."""
+    import torch
+    n = len(efs)
+    cands = [ef.bandDetect(images, g, n) for g, ef in enumerate(efs)]
+    all_cand = torch.stack(cands, 0).contiguous()
+    outs = [ef.bandFinish(all_cand, g, n, want_descriptors=want_descriptors) for g, ef in enumerate(efs)]
+    kp, desc, counts = outs[0]
+    if desc is not None:
+        for o in outs[1:]:
+            desc = torch.maximum(desc, o[1])
+    return kp, desc, counts, outs

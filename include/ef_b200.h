@@ -137,6 +137,26 @@ int ef_mg_detect_and_compute_host_batch(ef_mg_handle* m, int nframes, const uint
                                         int width, int height, float* h_kpts5, uint8_t* h_desc, int* h_counts);
 const char* ef_mg_last_error_string(const ef_mg_handle* m);
 
+/* ---- one oversized frame over several GPUs (new; SURVEY 8e "one oversized frame", north_star "image tiles with halo").
+ * Every GPU holds the whole image (the caller broadcasts it: ncclBroadcast / torch.distributed.broadcast) and is band
+ * `shard` of `nshards`: it builds the whole pyramid but runs FAST/Harris, the radius NMS and the compaction only on its
+ * horizontal band of every level (score stage: + the NMS halo), keeps its local top-quota per level and packs it into
+ * d_cand (ef_band_candidate_bytes() per frame).  The caller all-gathers the candidate buffers of all GPUs in shard order
+ * ([nshards][nframes][bytes]; <= 8 B x nfeatures per GPU) and calls ef_band_finish_async, which re-selects the global
+ * top-quota (bit-identical to the single-GPU result), writes the FULL keypoint matrix on every GPU and the descriptors of
+ * this GPU's share of the keypoints (descriptor CTAs dealt round-robin), all other descriptor rows zero: an element-wise
+ * MAX all-reduce (uint8) of d_desc assembles the frame's descriptors on every GPU.  nshards == 1 degenerates to
+ * ef_detect_and_compute_batch_async.  Replaces the same reference entry (src/cuda_efficient_features.cpp:225-321). */
+size_t ef_band_candidate_bytes(const ef_handle* h);
+int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
+                         int width, int height, uint8_t* d_cand, void* stream);
+int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_all_cand,
+                         float* d_kpts, size_t kpts_stride, size_t kpts_pitch, uint8_t* d_desc, size_t desc_stride, size_t desc_pitch,
+                         int* d_counts, void* stream);
+/* host arithmetic of the band partition: tile rows (32 pixel rows each) of a level with `tiles_y` tile rows owned by `shard`
+ * and the rows its score stage covers with `halo_tiles` extra tile rows on either side */
+void ef_band_tile_rows(int tiles_y, int shard, int nshards, int halo_tiles, int* own0, int* own_n, int* score0, int* score_n);
+
 /* ---- introspection for stage-by-stage parity tests (not part of the reference API) ---------- */
 typedef struct ef_level_view {
     int width, height;

@@ -1,0 +1,64 @@
+"""One oversized frame cut into horizontal bands over several GPUs (ef_band_*): the band-sharded result must be
+bit-identical to the single-GPU result (which the parity tests pin against the oracle).  The collectives are emulated on one
+GPU here (concatenation = all-gather, element-wise maximum = MAX all-reduce); tests/test_multirank_cpu.py covers the host
+partition under gloo and bench.py --tiled exercises the real NCCL path."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(torch, oracle, w, h, nfeat, dtype_name, nshards, frames=1, **kw):
+    import efb200
+    from efb200 import tiling
+    dt = getattr(efb200, dtype_name)
+    imgs = np.stack([oracle.synth_frame(util.SEED + 77 + nshards, f, w, h) for f in range(frames)])
+    d = torch.from_numpy(imgs).cuda()
+    single = efb200.EfficientFeatures.create(nfeatures=nfeat, dtype=dt, max_width=w, max_height=h, max_batch=frames, **kw)
+    kp0, desc0, cnt0 = single.detectAndComputeBatchRaw(d)
+    torch.cuda.synchronize()
+    counts0 = np.stack([single.debugLevelCounts(f) for f in range(frames)])
+    efs = [efb200.EfficientFeatures.create(nfeatures=nfeat, dtype=dt, max_width=w, max_height=h, max_batch=frames, **kw) for _ in range(nshards)]
+    kp, desc, cnt, outs = tiling.detect_and_compute_tiled_emulated(efs, d)
+    torch.cuda.synchronize()
+    assert np.array_equal(cnt.cpu().numpy(), cnt0.cpu().numpy())
+    for f in range(frames):
+        n = int(cnt0[f])
+        assert n > 0
+        for g, o in enumerate(outs):   # the keypoint matrix is complete and identical on every band owner
+            assert np.array_equal(o[0][f, :, :n].cpu().numpy().view(np.uint32), kp0[f, :, :n].cpu().numpy().view(np.uint32)), f"keypoints differ on shard {g}"
+            assert np.array_equal(efs[g].debugLevelCounts(f), counts0[f]), f"per-level counts differ on shard {g}"
+        a, b = desc[f, :n].cpu().numpy(), desc0[f, :n].cpu().numpy()
+        assert np.array_equal(a, b), f"{(a != b).any(axis=1).sum()} of {n} descriptors differ"
+        # every row is produced by exactly one shard
+        nz = sum((o[1][f, :n] != 0).any(dim=1).int() for o in outs).cpu().numpy()
+        assert nz.max() <= 1
+    return int(cnt0.sum())
+
+
+@pytest.mark.parametrize("nshards", [1, 2, 3, 8])
+@pytest.mark.parametrize("dtype_name", ["BAD_512", "HASH_SIFT_256"])
+def test_band_sharded_equals_single_gpu(oracle, dtype_name, nshards):
+    import torch
+    _run(torch, oracle, 1280, 720, 3000, dtype_name, nshards)
+
+
+def test_band_sharded_more_shards_than_tile_rows(oracle):
+    import torch
+    # level 7 of a 300x200 frame has 2 tile rows: most of the 8 bands own nothing there
+    _run(torch, oracle, 300, 200, 500, "BAD_256", 8)
+
+
+@pytest.mark.parametrize("kw", [dict(nonmaxRadius=31), dict(nonmaxRadius=3), dict(nonmaxRadius=64, nlevels=4), dict(firstLevel=2)])
+def test_band_sharded_other_parameters(oracle, kw):
+    import torch
+    _run(torch, oracle, 900, 700, 2000, "BAD_256", 3, **kw)
+
+
+def test_band_sharded_batch_and_8k(oracle):
+    import torch
+    _run(torch, oracle, 800, 608, 1500, "HASH_SIFT_512", 2, frames=3)
+    n = _run(torch, oracle, 7680, 4320, 40000, "HASH_SIFT_512", 4)
+    assert n == 40000   # every per-level quota binds at 8K

@@ -55,3 +55,75 @@ def test_two_rank_sharding_gloo():
     o = efo.Oracle()
     single = [len(o.detect(o.synth_frame(0xEFB20000 + 3, f, 320, 240), o.make_params(nfeatures=300, desc_type=efo.BAD_256))[0]) for f in range(5)]
     assert single == res[0][2]
+
+
+# ---------------------------------------------------------------------------------------------------
+# one oversized frame over several ranks (efb200/tiling.py): band partition + the two collectives
+# ---------------------------------------------------------------------------------------------------
+def test_band_partition_covers_every_tile_row_once():
+    sys.path.insert(0, str(ROOT / "cuda-efficient-features_b200"))
+    from efb200.tiling import band_tile_rows
+    for tiles_y in (1, 2, 7, 19, 68, 135):
+        for n in (1, 2, 3, 4, 8):
+            for halo in (0, 1, 3):
+                owned = []
+                for g in range(n):
+                    o0, on, s0, sn = band_tile_rows(tiles_y, g, n, halo)
+                    owned += list(range(o0, o0 + on))
+                    if on == 0:
+                        assert sn == 0
+                    else:   # score rows = owned rows + halo, clipped to the level
+                        assert s0 == max(0, o0 - halo) and s0 + sn == min(tiles_y, o0 + on + halo)
+                assert owned == list(range(tiles_y)), (tiles_y, n)
+
+
+class _StubFeatures:
+    """Stands in for EfficientFeatures on CPU tensors: checks what the collectives deliver."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def bandDetect(self, images, shard, nshards, stream=None):
+        import torch
+        assert (shard, nshards) == (self.rank, self.world)
+        return torch.full((images.shape[0], 48), shard + 1, dtype=torch.uint8) + images[:, 0, :48]
+
+    def bandFinish(self, all_cand, shard, nshards, want_descriptors=True, out=None):
+        import torch
+        assert tuple(all_cand.shape) == (nshards, 2, 48)
+        for g in range(nshards):   # shard order, every rank's candidates
+            assert int(all_cand[g, 0, 0]) == g + 1 + 7
+        desc = torch.zeros((2, 10, 4), dtype=torch.uint8)
+        desc[:, shard::nshards] = 100 + shard
+        return torch.zeros((2, 5, 10)), desc, torch.full((2,), 10, dtype=torch.int32)
+
+
+def _band_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT / "cuda-efficient-features_b200"))
+    import torch
+    import torch.distributed as dist
+    from efb200.tiling import detect_and_compute_tiled
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    images = torch.full((2, 64, 64), 7 if rank == 0 else 0, dtype=torch.uint8)   # only the source rank has the frame
+    kp, desc, counts = detect_and_compute_tiled(_StubFeatures(rank, world), images, src=0)
+    q.put((rank, desc[0, :, 0].tolist(), int(images[1, 5, 5])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_collectives_gloo():
+    world, port = 2, 29741
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_band_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rows, px in res:
+        assert px == 7                                      # image broadcast from rank 0
+        assert rows == [100, 101] * 5                       # MAX all-reduce assembled the rows of both ranks
