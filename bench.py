@@ -121,6 +121,9 @@ def main():
     ap.add_argument("--desc", default="HASH_SIFT_512", choices=list(DESC))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tiled", action="store_true",
+                    help="instead of sharding frames, cut EVERY frame into horizontal bands over the ranks (ef_band_*): image broadcast from "
+                         "rank 0, all-gather of the band candidates and MAX all-reduce of the descriptors inside the timed region; strong scaling")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -130,7 +133,9 @@ def main():
     config = {"workload": f"detectAndCompute {args.desc} on {args.width}x{args.height} synthetic uniform-noise frames, nfeatures {args.nfeatures}, "
                           f"8 levels x1.2, FAST th 20, NMS r 15 (BASELINE.json configs[3]/[4] at the 4K metric resolution)",
               "width": args.width, "height": args.height, "nfeatures": args.nfeatures, "descriptor": args.desc,
-              "frames_per_gpu_per_step": args.batch, "sharding": f"frames over {world} rank(s), no collective on the data path",
+              "frames_per_gpu_per_step": args.batch,
+              "sharding": (f"every frame cut into {world} horizontal band(s) with NMS halo; NCCL broadcast of the image, all-gather of band candidates, "
+                           f"MAX all-reduce of descriptors" if args.tiled else f"frames over {world} rank(s), no collective on the data path"),
               "l2_policy": f"batch of {args.batch} frames = {args.batch * args.width * args.height / 1e6:.0f} MB input + >1 GB intermediates per step, larger than the 126 MB L2"}
 
     if args.impl == "reference":
@@ -171,8 +176,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.tiled:
+        from efb200 import tiling
+        def step():
+            tiling.detect_and_compute_tiled(ef, frames, src=0 if world > 1 else None, out=out)
+    else:
+        def step():
+            ef.detectAndComputeBatchRaw(frames, out=out)
+
     for _ in range(args.warmup):
-        ef.detectAndComputeBatchRaw(frames, out=out)
+        step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -184,7 +197,7 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        ef.detectAndComputeBatchRaw(frames, out=out)
+        step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -200,12 +213,16 @@ def main():
         ms = float(tmax[0].item()); nk_total = float(tsum[1].item())
     else:
         nk_total = float(nk)
-    value = world * B * args.steps * W * H / (ms * 1e-3) / 1e6
-    kps = nk_total * args.steps / (ms * 1e-3)
+    if args.tiled:   # the same B frames on every rank: total work is fixed
+        value = B * args.steps * W * H / (ms * 1e-3) / 1e6
+        kps = float(nk) * args.steps / (ms * 1e-3)
+    else:
+        value = world * B * args.steps * W * H / (ms * 1e-3) / 1e6
+        kps = nk_total * args.steps / (ms * 1e-3)
 
     # ---- e2e: same metric through the host-buffer C-ABI call (H2D of the frames + D2H of keypoints/descriptors inside)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.tiled:
         kp_h = torch.empty((B, 5, args.nfeatures), dtype=torch.float32).pin_memory()
         desc_h = torch.empty((B, args.nfeatures, dbytes), dtype=torch.uint8).pin_memory()
         for _ in range(min(args.warmup, 3)):
@@ -235,7 +252,7 @@ def main():
            "angle_pack": n_frame * (709 + 20), "blur": 2 * P, "describe": n_frame * (1024 + 16 + (dbytes if dtype_id < 2 else 128)),
            "project": n_frame * (128 + dbytes)}
     peak, peak_kind = measured_peak()
-    per_call = {k: v / max(ncalls, 1) for k, v in stage_ms.items()}
+    per_call = {k: v / max(args.steps, 1) for k, v in stage_ms.items()}   # per step (a tiled step is two C-ABI calls)
     dom = max(per_call, key=per_call.get)
     def roof(stage):
         ach = alg[stage] * B / (per_call[stage] * 1e-3) / 1e9 if per_call[stage] > 0 else 0.0
@@ -267,7 +284,7 @@ def main():
                         "single_thread_value": r1["value"], "keypoints_per_s": r["keypoints_per_s"]}
 
     line = {"metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.tiled else "weak", "vs_baseline": None, "dtype": "u8/f32",
             "data": "synthetic", "config": config, "frames_per_s": value * 1e6 / (W * H), "keypoints_per_s": kps,
             "keypoints_per_frame": n_frame, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_pyramid": roofline_pyr, "stage_ms_per_step": per_call,
