@@ -37,6 +37,8 @@ EXPORTS = [
     "ef_mg_create", "ef_mg_destroy", "ef_mg_device_count", "ef_mg_shard_range", "ef_mg_detect_and_compute_host_batch",
     "ef_mg_last_error_string",
     "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows",
+    "ef_match_scratch_bytes", "ef_match_knn_async", "ef_match_cross_check_async", "ef_match_ratio_cross_async",
+    "ef_match_last_error_string", "ef_bgr_to_gray_async",
 ]
 STAGE_NAMES = ["pyramid", "score", "nms", "compact", "select", "angle_pack", "blur", "describe", "project"]
 
@@ -112,6 +114,13 @@ def load_library() -> C.CDLL:
     L.ef_band_finish_async.argtypes = [vp, i32, i32, i32, vp, vp, sz, sz, vp, sz, sz, vp, vp]
     L.ef_band_tile_rows.argtypes = [i32, i32, i32, i32] + [C.POINTER(i32)] * 4
     L.ef_band_tile_rows.restype = None
+    L.ef_match_scratch_bytes.argtypes = [i32, i32]
+    L.ef_match_scratch_bytes.restype = sz
+    L.ef_match_knn_async.argtypes = [vp, sz, i32, vp, sz, i32, i32, i32, vp, vp, vp, vp]
+    L.ef_match_cross_check_async.argtypes = [vp, sz, i32, vp, sz, i32, i32, vp, vp, vp, vp]
+    L.ef_match_ratio_cross_async.argtypes = [vp, vp, i32, vp, vp, i32, C.c_double, vp, vp]
+    L.ef_match_last_error_string.restype = C.c_char_p
+    L.ef_bgr_to_gray_async.argtypes = [vp, sz, i32, i32, i32, vp, sz, vp]
     _lib = L
     return L
 
@@ -578,3 +587,7 @@ class HashSIFT(_Describer):
         if nbits not in (100, 101):
             raise EfError("n_bits should be either SIZE_512_BITS or SIZE_256_BITS")
         return HashSIFT(HASH_SIFT_512 if nbits == 100 else HASH_SIFT_256, croppingScale, max_width, max_height, max_keypoints, device)
+
+
+# ---- callers either side of the path: matcher and colour conversion (efb200/matching.py) ----
+from .matching import BFMatcher, DMATCH_DTYPE, cvtColorToGray, ratio_cross_filter  # noqa: E402,F401

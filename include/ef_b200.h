@@ -157,6 +157,29 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
  * and the rows its score stage covers with `halo_tiles` extra tile rows on either side */
 void ef_band_tile_rows(int tiles_y, int shard, int nshards, int halo_tiles, int* own0, int* own_n, int* score0, int* score_n);
 
+/* ---- callers either side of the path ------------------------------------------------------------
+ * Brute-force Hamming matcher on the descriptors the path produced (32- or 64-byte rows), stateless.
+ * ef_match_knn_async replaces cv::BFMatcher(NORM_HAMMING)::knnMatch(query, train, matches, k) for k = 1 or 2
+ * (samples/sample_image_sequence.cpp:81,115-116): d_idx / d_dist are nq x k ints, row q = the k lexicographically smallest
+ * (distance, trainIdx) pairs (OpenCV's order); missing entries (nt < k) are idx -1.
+ * ef_match_cross_check_async replaces cv::BFMatcher::create(NORM_HAMMING, true)->match (samples/sample_feature_matching.cpp:99-101):
+ * d_train_idx[q] = the train row matched to query q, or -1 (OpenCV omits those queries from the match list).
+ * ef_match_ratio_cross_async is the filter loop of samples/sample_image_sequence.cpp:121-137 over two k = 2 results:
+ * d_out_train[q] = matched train row or -1.
+ * d_scratch: ef_match_scratch_bytes(nq, nt) bytes of device memory owned by the caller (no hidden allocation). */
+size_t ef_match_scratch_bytes(int nq, int nt);
+int ef_match_knn_async(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes, int k,
+                       int* d_idx, int* d_dist, void* d_scratch, void* stream);
+int ef_match_cross_check_async(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes,
+                               int* d_train_idx, int* d_dist, void* d_scratch, void* stream);
+int ef_match_ratio_cross_async(const int* d_idx12, const int* d_dist12, int nq, const int* d_idx21, const int* d_dist21, int nt,
+                               double uniqueness, int* d_out_train, void* stream);
+const char* ef_match_last_error_string(void);
+/* replaces convertToGray (samples/sample_common.cpp:35-45: cv::cvtColor COLOR_BGR2GRAY / COLOR_BGRA2GRAY): interleaved 8-bit
+ * BGR (channels 3) or BGRA (4) device image -> CV_8UC1, OpenCV's 15-bit fixed-point weights */
+int ef_bgr_to_gray_async(const uint8_t* d_src, size_t src_pitch, int width, int height, int channels,
+                         uint8_t* d_gray, size_t gray_pitch, void* stream);
+
 /* ---- introspection for stage-by-stage parity tests (not part of the reference API) ---------- */
 typedef struct ef_level_view {
     int width, height;
