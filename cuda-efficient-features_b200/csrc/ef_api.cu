@@ -122,6 +122,7 @@ struct ef_handle {
     unsigned char* d_bad_radius[2] = { nullptr, nullptr };
     float* d_bad_thr[2] = { nullptr, nullptr };
     float* d_hs_weights_t[2] = { nullptr, nullptr }; // 129 x nbits (transposed; fp64 fallback projection)
+    uint8_t* d_hs_btc[2] = { nullptr, nullptr };     // the same digits in UMMA core-matrix order for tcgen05 (ef_project_tc.cu)
     uint4* d_hs_bfrag[2] = { nullptr, nullptr };     // fixed-point digits of the projection in mma fragment order (ef_project.cu)
     long long* d_hs_bias[2] = { nullptr, nullptr };  // column 0 of the projection as fixed-point integers
     int hs_shift[2] = { 0, 0 };                      // fixed-point scale 2^-shift; bfrag == nullptr: table does not fit 6 digits
@@ -180,7 +181,7 @@ int fail(ef_handle* h, int code, const std::string& msg)
 void free_all(ef_handle* h)
 {
     cudaFree(h->d_ws); cudaFree(h->d_counters);
-    for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); cudaFree(h->d_hs_bfrag[i]); cudaFree(h->d_hs_bias[i]); }
+    for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); cudaFree(h->d_hs_bfrag[i]); cudaFree(h->d_hs_btc[i]); cudaFree(h->d_hs_bias[i]); }
     cudaFree(h->d_exp_table); cudaFree(h->d_grad_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
     cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
     cudaFree(h->d_in); cudaFree(h->d_out_kpts); cudaFree(h->d_out_desc); cudaFree(h->d_out_counts);
@@ -322,6 +323,17 @@ int upload_tables(ef_handle* h)
                 EF_CUDA(h, cudaMemcpy(h->d_hs_bfrag[v], frag.data(), frag.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
                 EF_CUDA(h, cudaMemcpy(h->d_hs_bias[v], bias.data(), bias.size() * sizeof(long long), cudaMemcpyHostToDevice));
                 h->hs_shift[v] = S;
+                // tcgen05 operand order: btc[chunk of 32 output bits][digit][4 KB], inside a 4 KB block the UMMA no-swizzle K-major
+                // core-matrix layout: (n / 8) * 1024 + (k / 16) * 128 + (n % 8) * 16 + (k % 16)
+                std::vector<signed char> btc((size_t)6 * nbits * 128);
+                for (int j = 0; j < nbits; j++)
+                    for (int d = 0; d < 6; d++)
+                        for (int k = 0; k < 128; k++) {
+                            const int c = j / 32, nl = j % 32;
+                            btc[((size_t)c * 6 + d) * 4096 + (nl / 8) * 1024 + (k / 16) * 128 + (nl % 8) * 16 + (k % 16)] = dig[((size_t)d * nbits + j) * 128 + k];
+                        }
+                EF_CUDA(h, cudaMalloc(&h->d_hs_btc[v], btc.size()));
+                EF_CUDA(h, cudaMemcpy(h->d_hs_btc[v], btc.data(), btc.size(), cudaMemcpyHostToDevice));
             }
         }
     }
@@ -502,7 +514,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
             EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
-            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
             ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, P.desc_bytes * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, h->keep_proj ? h->d_proj : nullptr, s);
             mark(h, EF_STAGE_PROJECT, s);
@@ -663,7 +675,7 @@ static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int 
     } else {
         EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
         ef_launch_hashsift_features_flat(job, t, h->d_sift128, s);
-        const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+        const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
         ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, pt, job.nbits, d_desc, 0, (int)desc_pitch,
                                          h->keep_proj ? h->d_proj : nullptr, s);
     }
@@ -834,7 +846,7 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
             EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
-            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v] };
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
             ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, db * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, nullptr, s);
             if (nshards > 1) ef_launch_band_mask_rows(P, true, s);

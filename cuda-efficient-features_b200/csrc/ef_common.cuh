@@ -150,7 +150,10 @@ void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTabl
 void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s);
 // projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8).  bfrag != nullptr: exact integer-tensor-core
 // path (fixed-point digits of the weights in mma fragment order, int64 bias, scale 2^-shift); else fp64 fallback on weights_t.
-struct EfProjTables { const uint4* bfrag; const long long* bias; int shift; const float* weights_t; /*129 x nbits*/ };
+struct EfProjTables { const uint4* bfrag; const long long* bias; int shift; const float* weights_t; /*129 x nbits*/
+                      const uint8_t* btc; /* digits in UMMA core-matrix order for the tcgen05 path (ef_project_tc.cu), or nullptr */ };
+bool ef_launch_hashsift_project_tc(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
+                                   uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s);
 void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const EfProjTables& t, int nbits,
                                 uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s);
 void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
