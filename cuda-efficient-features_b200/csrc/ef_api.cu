@@ -897,6 +897,21 @@ int ef_debug_hashsift_views(const ef_handle* h, const uint8_t** d_sift128, const
     return EF_OK;
 }
 
+int ef_debug_project_async(ef_handle* h, const uint8_t* d_sift128, int n, int path, uint8_t* d_desc, size_t desc_pitch, void* stream)
+{
+    if (!h || !d_sift128 || !d_desc || n < 0 || path < 0 || path > 3) return EF_ERR_BAD_ARG;
+    if (is_bad(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "the handle's descriptor type is not HashSIFT");
+    if (n == 0) return EF_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    const int db = desc_bytes_of(h->prm.desc_type), v = db == 32 ? 0 : 1;
+    const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
+    g_ef_project_path = path;   // tests only: not thread safe
+    ef_launch_hashsift_project_batch(d_sift128, n, nullptr, 1, pt, db * 8, d_desc, 0, (int)desc_pitch, nullptr, (cudaStream_t)stream);
+    g_ef_project_path = 0;
+    EF_CUDA(h, cudaGetLastError());
+    return EF_OK;
+}
+
 int ef_stage_timing_enable(ef_handle* h, int enable)
 {
     if (!h) return EF_ERR_BAD_ARG;

@@ -154,6 +154,7 @@ struct EfProjTables { const uint4* bfrag; const long long* bias; int shift; cons
                       const uint8_t* btc; /* digits in UMMA core-matrix order for the tcgen05 path (ef_project_tc.cu), or nullptr */ };
 bool ef_launch_hashsift_project_tc(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
                                    uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s);
+extern int g_ef_project_path;
 void ef_launch_hashsift_project(const uint8_t* sift128, int n_cap, const int* d_n, const EfProjTables& t, int nbits,
                                 uint8_t* desc, int desc_pitch, float* proj_out, cudaStream_t s);
 void ef_launch_hashsift_project_batch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,

@@ -204,16 +204,19 @@ __global__ void __launch_bounds__(256) ef_hashsift_project_kernel(const uint8_t*
     }
 }
 
+int g_ef_project_path = 0;   // 0: default (tcgen05, EF_PROJECT=imma -> mma.sync); ef_debug_project_async forces 1 = tcgen05, 2 = mma.sync, 3 = fp64
+
 static void ef_project_launch(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
                               uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s)
 {
     // EF_PROJECT=imma keeps the mma.sync kernel (A/B comparison); default: tcgen05 (ef_project_tc.cu)
-    static const bool use_tc = [] { const char* e = getenv("EF_PROJECT"); return !(e && e[0] == 'i'); }();
+    static const bool env_tc = [] { const char* e = getenv("EF_PROJECT"); return !(e && e[0] == 'i'); }();
+    const bool use_tc = g_ef_project_path == 0 ? env_tc : g_ef_project_path == 1;
     if (use_tc && t.btc && ef_launch_hashsift_project_tc(sift128, n_cap, d_counts, nframes, t, nbits, desc, desc_stride, desc_pitch, proj_out, s)) {
         EF_COUNT_LAUNCH(1);
         return;
     }
-    if (t.bfrag) {
+    if (t.bfrag && g_ef_project_path != 3) {
         const dim3 grid(ef_div_up(n_cap, EF_PJ_WARPS * EF_PJ_ROWS_PER_WARP), nframes);
         ef_hashsift_project_imma_kernel<<<grid, EF_PJ_WARPS * 32, 0, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, t.bfrag, t.bias, t.shift, nbits / 8,
                                                                          desc, desc_stride, desc_pitch, proj_out);

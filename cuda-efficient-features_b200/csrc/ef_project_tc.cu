@@ -5,15 +5,19 @@
 //   * A (128 keypoint rows x 128 k, u8) and B (32 output bits x 128 k x 6 digits, s8) sit in shared memory in the UMMA
 //     no-swizzle K-major "core matrix" layout (8 rows x 16 bytes contiguous; LBO = 128 B between the k-halves of one MMA,
 //     SBO = 1024 B between 8-row groups); B is pre-packed in that byte order on the host and streamed with cp.async.
-//   * one elected thread issues 24 tcgen05.mma (M128 x N32 x K32, 6 digits x 4 k-steps) per 32 output bits; the six digit
-//     accumulators are 6 x 32 TMEM columns (256 columns allocated per CTA: two CTAs per SM share the 512 columns).
+//   * one elected thread issues 4 tcgen05.mma (M128 x N192 x K32: the six digit blocks of a chunk form ONE B operand) per 32
+//     output bits; the six digit accumulators are 6 x 32 TMEM columns (256 columns allocated per CTA: two CTAs per SM share the 512 columns).
 //   * completion comes back through tcgen05.commit -> mbarrier; the epilogue reads the accumulators with tcgen05.ld (thread =
-//     keypoint row, TMEM lane = row), recombines in int64 and writes 32 descriptor bits with one store.
+//     keypoint row x half of the chunk's columns, TMEM lane = row), recombines in int64 and writes 16 descriptor bits per store.
 //   * the next 24 KB of B digits are in flight (cp.async double buffer) while the tensor core and the epilogue run.
 // Every spin on the mbarrier is bounded (trap instead of a hung GPU if a descriptor were ever wrong).
 #include "ef_common.cuh"
 
 #define EF_TC_ROWS 128               // keypoint rows per CTA (= UMMA M = TMEM lanes)
+#ifndef EF_TC_THREADS
+#define EF_TC_THREADS 128            // 128: one thread per row (0.163 ms per 8 frames); 256: two threads per row, 16 output bits each (0.175 ms)
+#endif
+#define EF_TC_TPR (EF_TC_THREADS / EF_TC_ROWS)             // threads per row
 #define EF_TC_NCH 32                 // output bits per chunk (= UMMA N)
 #define EF_TC_DIGITS 6
 #define EF_TC_A_BYTES (EF_TC_ROWS * 128)
@@ -33,7 +37,8 @@ __device__ __forceinline__ unsigned long long ef_umma_desc(unsigned smem_addr, u
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 at [4,6)), A = U8 (0 at [7,10)), B = S8 (1 at [10,13)),
 // both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-#define EF_TC_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((unsigned)(EF_TC_NCH >> 3) << 17) | ((unsigned)(EF_TC_ROWS >> 4) << 24))
+#define EF_TC_UMMA_N (EF_TC_DIGITS * EF_TC_NCH)           // 192: the six digit blocks are adjacent 8-row groups of ONE B operand
+#define EF_TC_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((unsigned)(EF_TC_UMMA_N >> 3) << 17) | ((unsigned)(EF_TC_ROWS >> 4) << 24))
 
 __device__ __forceinline__ void ef_tc_mma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned accumulate)
 {
@@ -53,7 +58,7 @@ __device__ __forceinline__ void ef_tc_cp_async16(unsigned smem, const void* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
 
-__global__ void __launch_bounds__(EF_TC_ROWS, 2)
+__global__ void __launch_bounds__(EF_TC_THREADS, 2)
 ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, const int* __restrict__ d_n, size_t frame_rows,
                               const uint8_t* __restrict__ btc, const long long* __restrict__ bias, int S, int nchunks,
                               uint8_t* __restrict__ desc, size_t desc_stride, int desc_pitch, float* __restrict__ proj_out)
@@ -68,6 +73,7 @@ ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, co
     const int row0 = blockIdx.x * EF_TC_ROWS;
     if (row0 >= n) return;                                   // CTA-uniform, before any allocation
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int rl = tid & (EF_TC_ROWS - 1), hf = tid >> 7;     // row of the tile, half of the chunk's columns (warps w and w + 4 share TMEM lanes)
     const unsigned sA = ef_smem_u32(s_dyn), sB = sA + EF_TC_A_BYTES;
     const unsigned mbar = ef_smem_u32(&s_mbar);
 
@@ -80,16 +86,16 @@ ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, co
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < nchunks * EF_TC_NCH; i += EF_TC_ROWS) s_bias[i] = bias[i];
-    for (int i = tid; i < EF_TC_B_BYTES / 16; i += EF_TC_ROWS) ef_tc_cp_async16(sB + 16 * i, btc + 16 * (size_t)i);
+    for (int i = tid; i < nchunks * EF_TC_NCH; i += EF_TC_THREADS) s_bias[i] = bias[i];
+    for (int i = tid; i < EF_TC_B_BYTES / 16; i += EF_TC_THREADS) ef_tc_cp_async16(sB + 16 * i, btc + 16 * (size_t)i);
     asm volatile("cp.async.commit_group;" ::: "memory");
     {
-        // thread = row: 8 chunks of 16 k-bytes -> (row / 8) * 1024 + chunk * 128 + (row % 8) * 16
-        const int r = row0 + tid;
-        const uint4* src = reinterpret_cast<const uint4*>(sift128 + ((size_t)frame * frame_rows + min(r, n - 1)) * 128);
-        uint8_t* dstA = s_dyn + (tid >> 3) * 1024 + (tid & 7) * 16;
+        // EF_TC_TPR threads per row, 8 / EF_TC_TPR chunks of 16 k-bytes each -> (row / 8) * 1024 + chunk * 128 + (row % 8) * 16
+        const int r = row0 + rl;
+        const uint4* src = reinterpret_cast<const uint4*>(sift128 + ((size_t)frame * frame_rows + min(r, n - 1)) * 128) + (8 / EF_TC_TPR) * hf;
+        uint8_t* dstA = s_dyn + (rl >> 3) * 1024 + (rl & 7) * 16 + (8 / EF_TC_TPR) * hf * 128;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < 8 / EF_TC_TPR; c++) {
             uint4 v = __ldg(src + c);
             if (r >= n) v = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(dstA + c * 128) = v;
@@ -103,20 +109,19 @@ ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, co
     const unsigned tmem = s_tmem;
 
     const float unscale = __int_as_float((127 - S) << 23);    // 2^-S
-    const int row = row0 + tid;
+    const int row = row0 + rl;
     uint8_t* out = desc + (size_t)frame * desc_stride + (size_t)row * desc_pitch;
-    const bool word_ok = ((reinterpret_cast<uintptr_t>(desc) | desc_stride | (size_t)desc_pitch) & 3) == 0;
+    const bool half_ok = ((reinterpret_cast<uintptr_t>(desc) | desc_stride | (size_t)desc_pitch) & 1) == 0;
     const int nbits = nchunks * EF_TC_NCH;
 
     for (int c = 0; c < nchunks; c++) {
         const unsigned sBc = sB + (c & 1) * EF_TC_B_BYTES;
         if (tid == 0) {
-            // 6 digits x 4 k-steps of M128 x N32 x K32; digit d accumulates into TMEM columns [32 d, 32 d + 32)
+            // 4 k-steps of M128 x N192 x K32: the six 32-row digit blocks of the chunk are contiguous in shared memory (4 KB each =
+            // four 8-row groups of SBO bytes), so one MMA covers all digits; digit d lands in TMEM columns [32 d, 32 d + 32)
 #pragma unroll
-            for (int d = 0; d < EF_TC_DIGITS; d++)
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++)
-                    ef_tc_mma_i8(tmem + 32 * d, ef_umma_desc(sA + ks * 256, 128, 1024), ef_umma_desc(sBc + d * EF_TC_BD_BYTES + ks * 256, 128, 1024), ks > 0);
+            for (int ks = 0; ks < 4; ks++)
+                ef_tc_mma_i8(tmem, ef_umma_desc(sA + ks * 256, 128, 1024), ef_umma_desc(sBc + ks * 256, 128, 1024), ks > 0);
             // arrives on the mbarrier when all MMAs above have completed (implies tcgen05.fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
         }
@@ -124,7 +129,7 @@ ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, co
             // next chunk's digits into the other buffer (its last reader, the MMAs of chunk c-1, completed before the previous wait returned)
             const uint8_t* g = btc + (size_t)(c + 1) * EF_TC_B_BYTES;
             const unsigned sBn = sB + ((c + 1) & 1) * EF_TC_B_BYTES;
-            for (int i = tid; i < EF_TC_B_BYTES / 16; i += EF_TC_ROWS) ef_tc_cp_async16(sBn + 16 * i, g + 16 * (size_t)i);
+            for (int i = tid; i < EF_TC_B_BYTES / 16; i += EF_TC_THREADS) ef_tc_cp_async16(sBn + 16 * i, g + 16 * (size_t)i);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         {
@@ -137,28 +142,30 @@ ef_hashsift_project_tc_kernel(const uint8_t* __restrict__ sift128, int n_cap, co
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- epilogue: thread = row = TMEM lane (warp w owns lanes 32 w .. 32 w + 31), two halves of 16 columns
-        unsigned word = 0;
+        // ---- epilogue: TMEM lane = row (warps w and w + 4 own lanes 32 (w % 4) .. + 31), thread = 16 of the chunk's 32 columns
 #pragma unroll
-        for (int hf = 0; hf < 2; hf++) {
+        for (int hh = 0; hh < 2 / EF_TC_TPR; hh++) {
+            const int h2 = EF_TC_TPR == 2 ? hf : hh;         // which 16 columns of the chunk
+            unsigned bits = 0;
             int a[EF_TC_DIGITS][16];
 #pragma unroll
-            for (int d = 0; d < EF_TC_DIGITS; d++) ef_tc_ld16(tmem + ((unsigned)(32 * warp) << 16) + 32 * d + 16 * hf, a[d]);
+            for (int d = 0; d < EF_TC_DIGITS; d++) ef_tc_ld16(tmem + ((unsigned)(32 * (warp & 3)) << 16) + 32 * d + 16 * h2, a[d]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const int t01 = a[0][j] + a[1][j] * 256;
                 const int t23 = a[2][j] + a[3][j] * 256;
                 const int t45 = a[4][j] + a[5][j] * 256;
-                const int jj = 16 * hf + j;
+                const int jj = 16 * h2 + j;
                 const long long tot = (long long)t01 + ((long long)t23 << 16) + ((long long)t45 << 32) + s_bias[c * EF_TC_NCH + jj];
-                word |= (tot > 0 ? 1u : 0u) << (8 * (jj >> 3) + 7 - (jj & 7));      // MSB first inside every byte
+                bits |= (tot > 0 ? 1u : 0u) << (8 * (j >> 3) + 7 - (j & 7));        // MSB first inside every byte
                 if (proj_out && row < n) proj_out[((size_t)frame * frame_rows + row) * nbits + c * EF_TC_NCH + jj] = __ll2float_rn(tot) * unscale;
             }
-        }
-        if (row < n) {
-            if (word_ok) *reinterpret_cast<unsigned*>(out + 4 * c) = word;
-            else { out[4 * c] = (uint8_t)word; out[4 * c + 1] = (uint8_t)(word >> 8); out[4 * c + 2] = (uint8_t)(word >> 16); out[4 * c + 3] = (uint8_t)(word >> 24); }
+            if (row < n) {
+                uint8_t* o = out + 4 * c + 2 * h2;
+                if (half_ok) *reinterpret_cast<unsigned short*>(o) = (unsigned short)bits;
+                else { o[0] = (uint8_t)bits; o[1] = (uint8_t)(bits >> 8); }
+            }
         }
         // the next chunk's MMAs overwrite the accumulators and read the freshly copied digits
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -182,7 +189,7 @@ bool ef_launch_hashsift_project_tc(const uint8_t* sift128, int n_cap, const int*
         __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
     }
     const dim3 grid(ef_div_up(n_cap, EF_TC_ROWS), nframes);
-    ef_hashsift_project_tc_kernel<<<grid, EF_TC_ROWS, EF_TC_SMEM, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, t.btc, t.bias, t.shift, nbits / EF_TC_NCH,
+    ef_hashsift_project_tc_kernel<<<grid, EF_TC_THREADS, EF_TC_SMEM, s>>>(sift128, n_cap, d_counts, (size_t)n_cap, t.btc, t.bias, t.shift, nbits / EF_TC_NCH,
                                                                       desc, desc_stride, desc_pitch, proj_out);
     return true;
 }

@@ -38,7 +38,7 @@ EXPORTS = [
     "ef_mg_last_error_string",
     "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows",
     "ef_match_scratch_bytes", "ef_match_knn_async", "ef_match_cross_check_async", "ef_match_ratio_cross_async",
-    "ef_match_last_error_string", "ef_bgr_to_gray_async",
+    "ef_match_last_error_string", "ef_bgr_to_gray_async", "ef_debug_project_async",
 ]
 STAGE_NAMES = ["pyramid", "score", "nms", "compact", "select", "angle_pack", "blur", "describe", "project"]
 
@@ -121,6 +121,7 @@ def load_library() -> C.CDLL:
     L.ef_match_ratio_cross_async.argtypes = [vp, vp, i32, vp, vp, i32, C.c_double, vp, vp]
     L.ef_match_last_error_string.restype = C.c_char_p
     L.ef_bgr_to_gray_async.argtypes = [vp, sz, i32, i32, i32, vp, sz, vp]
+    L.ef_debug_project_async.argtypes = [vp, vp, i32, i32, vp, sz, vp]
     _lib = L
     return L
 
@@ -486,6 +487,14 @@ class EfficientFeatures:
         buf = (C.c_int * (3 * n))()
         self._h.check(self._h.L.ef_debug_level_counts(self._h.h, frame, buf, _stream_ptr(None)))
         return np.array(list(buf)).reshape(n, 3)
+
+    def debugProject(self, sift128, path=0):
+        """The projection stage alone: n x 128 uint8 CUDA tensor -> n x descriptorSize() bits; path 1 = tcgen05, 2 = mma.sync, 3 = fp64."""
+        torch = _torch()
+        assert sift128.is_cuda and sift128.dtype == torch.uint8 and sift128.dim() == 2 and sift128.shape[1] == 128 and sift128.is_contiguous()
+        desc = torch.empty((sift128.shape[0], self.descriptorSize()), dtype=torch.uint8, device=sift128.device)
+        self._h.check(self._h.L.ef_debug_project_async(self._h.h, sift128.data_ptr(), sift128.shape[0], path, desc.data_ptr(), desc.stride(0), _stream_ptr(None)))
+        return desc
 
     def debugKeepProjection(self, keep=True):
         self._h.check(self._h.L.ef_debug_keep_projection(self._h.h, int(keep)))

@@ -199,6 +199,9 @@ int ef_debug_level_counts(ef_handle* h, int frame, int* h_counts3, void* stream)
  * (projection only kept when ef_debug_keep_projection(h,1) was set before the call) */
 int ef_debug_keep_projection(ef_handle* h, int keep);
 int ef_debug_hashsift_views(const ef_handle* h, const uint8_t** d_sift128, const float** d_projection);
+/* the projection stage alone on caller-provided SIFT vectors (n x 128 uint8, 16-byte aligned): path 0 = default, 1 = tcgen05,
+ * 2 = mma.sync, 3 = fp64 CUDA cores (1 and 2: the exact six-digit integer GEMM).  Tests only, not thread safe. */
+int ef_debug_project_async(ef_handle* h, const uint8_t* d_sift128, int n, int path, uint8_t* d_desc, size_t desc_pitch, void* stream);
 /* blocking device->host 2-D copy of one of the views above (tests only) */
 int ef_debug_copy_to_host(ef_handle* h, void* dst, size_t dst_pitch, const void* d_src, size_t src_pitch,
                           size_t width_bytes, size_t rows);

@@ -370,3 +370,29 @@ def test_single_process_multi_gpu_driver(torch_cuda, oracle):
     ok, od, _ = oracle.detect_and_compute(frames[F - 1], oracle.make_params(nfeatures=1200, desc_type=efo.BAD_512))
     util.assert_keypoints_equal(efb200.EfficientFeatures.convert(kps[F - 1]), util.oracle_to_struct(ok))
     mg.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the projection stage alone: tcgen05 == mma.sync (both the exact six-digit integer GEMM) == fp64 CUDA cores
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype_name", ["HASH_SIFT_256", "HASH_SIFT_512"])
+def test_projection_paths_agree(torch_cuda, dtype_name):
+    import efb200
+    torch = torch_cuda
+    ef = make_ef(nfeatures=1000, dtype=getattr(efb200, dtype_name), max_width=640, max_height=480, max_keypoints=70000)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    cases = {
+        "uniform": torch.randint(0, 256, (60001, 128), dtype=torch.uint8, generator=g),
+        "sparse": (torch.randint(0, 256, (9000, 128), dtype=torch.uint8, generator=g) * (torch.rand((9000, 128), generator=g) < 0.1)).to(torch.uint8),
+        "zeros_and_max": torch.cat([torch.zeros((130, 128), dtype=torch.uint8), torch.full((130, 128), 255, dtype=torch.uint8)]),
+        "siftlike": torch.clamp((torch.randn((20000, 128), generator=g).abs() * 40), 0, 255).to(torch.uint8),
+        "tiny": torch.randint(0, 3, (5, 128), dtype=torch.uint8, generator=g),
+    }
+    for name, x in cases.items():
+        d = x.cuda().contiguous()
+        ref = ef.debugProject(d, 3).cpu().numpy()       # double accumulation of the fp32 table (the oracle's definition)
+        tc = ef.debugProject(d, 1).cpu().numpy()
+        imma = ef.debugProject(d, 2).cpu().numpy()
+        assert np.array_equal(imma, ref), f"{name}: mma.sync path differs from fp64 in {(imma != ref).any(axis=1).sum()} rows"
+        assert np.array_equal(tc, ref), f"{name}: tcgen05 path differs from fp64 in {(tc != ref).any(axis=1).sum()} rows"
+        assert np.array_equal(ef.debugProject(d, 0).cpu().numpy(), ref)
