@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 
 #define EF_MT_THREADS 128
 #define EF_MT_TILE 128          // train descriptors per shared-memory tile
@@ -177,6 +178,12 @@ __global__ void __launch_bounds__(256) ef_match_ratio_cross_kernel(const int* __
     out_train[q] = r;
 }
 
+// tcgen05 path (ef_match_tc.cu)
+size_t ef_match_tc_expanded_bytes(int n, int desc_bytes);
+int ef_match_tc_splits(int nq, int nt);
+void ef_match_tc_expand(const uint8_t* d_desc, size_t pitch, int n, int desc_bytes, uint8_t* d_out, cudaStream_t s);
+void ef_match_tc_knn(const uint8_t* qexp, int nq, const uint8_t* texp, int nt, int desc_bytes, int k, int4* d_partial, int* d_idx, int* d_dist, cudaStream_t s);
+
 namespace {
 int match_splits(int nq, int nt)
 {
@@ -189,13 +196,36 @@ int match_splits(int nq, int nt)
 thread_local char g_match_err[256] = "";
 int match_fail(int code, const char* msg) { std::snprintf(g_match_err, sizeof(g_match_err), "%s", msg); return code; }
 
-int knn_launch(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes, int k,
-               int* d_idx, int* d_dist, void* d_scratch, cudaStream_t s)
+// tensor-core path for problems that fill the machine; EF_MATCH=alu keeps the CUDA-core kernel (A/B comparison)
+bool match_use_tc(int nq, int nt)
+{
+    static const bool env_alu = [] { const char* e = getenv("EF_MATCH"); return e && e[0] == 'a'; }();
+    return !env_alu && nq >= 256 && nt >= 256;
+}
+
+// scratch layout: [partial lists][index/distance rows of the cross check][+-1 expansion of the query set][of the train set]
+struct MatchScratch { size_t partial, rows, qexp, texp, total; };
+MatchScratch match_scratch(int nq, int nt)
+{
+    MatchScratch m{};
+    const size_t mx = (size_t)std::max(std::max(nq, nt), 1);
+    const size_t alu = (size_t)std::max(match_splits(nq, nt) * (size_t)nq, match_splits(nt, nq) * (size_t)nt) * sizeof(int4);
+    const size_t tc = (size_t)std::max(2 * ef_match_tc_splits(nq, nt) * (size_t)nq, 2 * ef_match_tc_splits(nt, nq) * (size_t)nt) * sizeof(int4);
+    m.partial = 0;
+    m.rows = ef_align_up(std::max(alu, tc), 256);
+    m.qexp = m.rows + ef_align_up(4 * mx * sizeof(int), 256);
+    m.texp = m.qexp + ef_match_tc_expanded_bytes(nq, 64);
+    m.total = m.texp + ef_match_tc_expanded_bytes(nt, 64) + 256;
+    return m;
+}
+
+int knn_launch_alu(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes, int k,
+                   int* d_idx, int* d_dist, void* d_partial, cudaStream_t s)
 {
     const int splits = match_splits(nq, nt);
     const int rows = ef_div_up(ef_div_up(nt, splits), EF_MT_TILE) * EF_MT_TILE;
     const int nsplit = ef_div_up(nt, rows);
-    int4* partial = reinterpret_cast<int4*>(d_scratch);
+    int4* partial = reinterpret_cast<int4*>(d_partial);
     const dim3 grid(ef_div_up(nq, EF_MT_THREADS), nsplit);
     if (desc_bytes == 64) ef_match_knn2_kernel<16><<<grid, EF_MT_THREADS, 0, s>>>(d_query, qpitch, nq, d_train, tpitch, nt, rows, partial);
     else ef_match_knn2_kernel<8><<<grid, EF_MT_THREADS, 0, s>>>(d_query, qpitch, nq, d_train, tpitch, nt, rows, partial);
@@ -208,6 +238,7 @@ int match_check(const void* q, int nq, const void* t, int nt, int desc_bytes, co
     if (nq < 0 || nt < 0) return match_fail(EF_ERR_BAD_ARG, "negative row count");
     if (desc_bytes != 32 && desc_bytes != 64) return match_fail(EF_ERR_BAD_ARG, "descriptor size must be 32 or 64 bytes (descriptorSize() of the path)");
     if (nq > 0 && nt > 0 && (!q || !t || !a || !b || !scratch)) return match_fail(EF_ERR_BAD_ARG, "null pointer");
+    if (scratch && (reinterpret_cast<uintptr_t>(scratch) & 15)) return match_fail(EF_ERR_BAD_ARG, "scratch must be 16-byte aligned");
     return EF_OK;
 }
 } // namespace
@@ -218,11 +249,8 @@ const char* ef_match_last_error_string(void) { return g_match_err; }
 
 size_t ef_match_scratch_bytes(int nq, int nt)
 {
-    if (nq <= 0 || nt <= 0) return 16;
-    const size_t m = (size_t)std::max(nq, nt);
-    // forward + backward partial lists (<= 256 splits each, but splits * rows <= 16 * 148 * 128 + rows) and two index/distance rows
-    const size_t part = (size_t)std::max(match_splits(nq, nt) * (size_t)nq, match_splits(nt, nq) * (size_t)nt) * sizeof(int4);
-    return part + 4 * m * 2 * sizeof(int) + 256;
+    if (nq <= 0 || nt <= 0) return 256;
+    return match_scratch(nq, nt).total;
 }
 
 int ef_match_knn_async(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes, int k,
@@ -231,14 +259,21 @@ int ef_match_knn_async(const uint8_t* d_query, size_t qpitch, int nq, const uint
     int rc = match_check(d_query, nq, d_train, nt, desc_bytes, d_idx, d_dist, d_scratch);
     if (rc != EF_OK) return rc;
     if (k != 1 && k != 2) return match_fail(EF_ERR_UNSUPPORTED, "k must be 1 or 2");
+    cudaStream_t s = (cudaStream_t)stream;
     if (nq == 0) return EF_OK;
     if (nt == 0) {
-        cudaMemsetAsync(d_idx, 0xff, sizeof(int) * (size_t)nq * k, (cudaStream_t)stream);
-        cudaMemsetAsync(d_dist, 0x7f, sizeof(int) * (size_t)nq * k, (cudaStream_t)stream); // 0x7f7f7f7f: "no match" distances are never read
+        cudaMemsetAsync(d_idx, 0xff, sizeof(int) * (size_t)nq * k, s);
+        cudaMemsetAsync(d_dist, 0x7f, sizeof(int) * (size_t)nq * k, s); // 0x7f7f7f7f: "no match" distances are never read
         return EF_OK;
     }
     if (qpitch < (size_t)desc_bytes || tpitch < (size_t)desc_bytes) return match_fail(EF_ERR_BAD_ARG, "pitch smaller than the descriptor size");
-    return knn_launch(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, k, d_idx, d_dist, d_scratch, (cudaStream_t)stream);
+    uint8_t* sc = reinterpret_cast<uint8_t*>(d_scratch);
+    if (!match_use_tc(nq, nt)) return knn_launch_alu(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, k, d_idx, d_dist, sc, s);
+    const MatchScratch m = match_scratch(nq, nt);
+    ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, sc + m.qexp, s);
+    ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, sc + m.texp, s);
+    ef_match_tc_knn(sc + m.qexp, nq, sc + m.texp, nt, desc_bytes, k, reinterpret_cast<int4*>(sc + m.partial), d_idx, d_dist, s);
+    return cudaGetLastError() == cudaSuccess ? EF_OK : match_fail(EF_ERR_CUDA, "kernel launch failed");
 }
 
 int ef_match_cross_check_async(const uint8_t* d_query, size_t qpitch, int nq, const uint8_t* d_train, size_t tpitch, int nt, int desc_bytes,
@@ -250,14 +285,22 @@ int ef_match_cross_check_async(const uint8_t* d_query, size_t qpitch, int nq, co
     if (nq == 0) return EF_OK;
     if (nt == 0) { cudaMemsetAsync(d_train_idx, 0xff, sizeof(int) * (size_t)nq, s); cudaMemsetAsync(d_dist, 0x7f, sizeof(int) * (size_t)nq, s); return EF_OK; }
     if (qpitch < (size_t)desc_bytes || tpitch < (size_t)desc_bytes) return match_fail(EF_ERR_BAD_ARG, "pitch smaller than the descriptor size");
-    const size_t m = (size_t)std::max(nq, nt);
-    const size_t part = (size_t)std::max(match_splits(nq, nt) * (size_t)nq, match_splits(nt, nq) * (size_t)nt) * sizeof(int4);
-    int* rows = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_scratch) + ef_align_up(part, 256));
-    int *fwd_idx = rows, *fwd_dist = rows + m, *bwd_idx = rows + 2 * m, *bwd_dist = rows + 3 * m;
-    rc = knn_launch(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, 1, fwd_idx, fwd_dist, d_scratch, s);
-    if (rc != EF_OK) return rc;
-    rc = knn_launch(d_train, tpitch, nt, d_query, qpitch, nq, desc_bytes, 1, bwd_idx, bwd_dist, d_scratch, s);
-    if (rc != EF_OK) return rc;
+    uint8_t* sc = reinterpret_cast<uint8_t*>(d_scratch);
+    const MatchScratch m = match_scratch(nq, nt);
+    const size_t mx = (size_t)std::max(nq, nt);
+    int* rows = reinterpret_cast<int*>(sc + m.rows);
+    int *fwd_idx = rows, *fwd_dist = rows + mx, *bwd_idx = rows + 2 * mx, *bwd_dist = rows + 3 * mx;
+    if (match_use_tc(nq, nt)) {
+        ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, sc + m.qexp, s);
+        ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, sc + m.texp, s);
+        ef_match_tc_knn(sc + m.qexp, nq, sc + m.texp, nt, desc_bytes, 1, reinterpret_cast<int4*>(sc + m.partial), fwd_idx, fwd_dist, s);
+        ef_match_tc_knn(sc + m.texp, nt, sc + m.qexp, nq, desc_bytes, 1, reinterpret_cast<int4*>(sc + m.partial), bwd_idx, bwd_dist, s);
+    } else {
+        rc = knn_launch_alu(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, 1, fwd_idx, fwd_dist, sc + m.partial, s);
+        if (rc != EF_OK) return rc;
+        rc = knn_launch_alu(d_train, tpitch, nt, d_query, qpitch, nq, desc_bytes, 1, bwd_idx, bwd_dist, sc + m.partial, s);
+        if (rc != EF_OK) return rc;
+    }
     ef_match_cross_kernel<<<ef_div_up(nq, 256), 256, 0, s>>>(fwd_idx, fwd_dist, bwd_idx, nq, d_train_idx, d_dist);
     EF_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? EF_OK : match_fail(EF_ERR_CUDA, "kernel launch failed");
