@@ -11,8 +11,8 @@
 //            of shared memory at K = 512, one CTA per SM).  One elected thread issues K / 32 M128 x N128 x K32 MMAs per tile into one
 //            of two 128-column TMEM accumulators: the tensor core works on tile t+1 while all 8 warps read tile t back (tcgen05.ld,
 //            thread = query row x half of the columns) and the TMA engine fetches tile t+2.
-//   select   per thread a running top-2 of (dot, index); a 64-value maximum (VIMNMX3 tree) filters out the tiles that cannot
-//            change it, so the common case costs half an instruction per pair.  Partial lists (one per split and column half) are
+//   select   per thread a running top-2 of (dot, index); the maximum of every 8 columns (VIMNMX3 tree) filters out the groups that
+//            cannot change it, so the common case costs half an instruction per pair.  Partial lists (one per split and column half) are
 //            merged lexicographically by ef_match_merge_lex_kernel.
 // Every mbarrier spin is bounded (trap instead of a hung GPU).
 #include "ef_common.cuh"
@@ -165,17 +165,19 @@ ef_match_tc_kernel(const uint8_t* __restrict__ qexp, int nq, const uint8_t* __re
             int a[32];
             ef_mtc_ld32(tl + 32 * part, a);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            int m = a[0];
+            // groups of 8 columns: a maximum (VIMNMX3) decides whether any of them can enter the top-2
 #pragma unroll
-            for (int j = 1; j < 32; j++) m = max(m, a[j]);
-            if (m > dot1) {
-                // some column may enter the top-2: columns arrive in increasing index, strict > keeps the earlier one on ties
+            for (int g = 0; g < 4; g++) {
+                const int m = max(max(max(a[8 * g], a[8 * g + 1]), max(a[8 * g + 2], a[8 * g + 3])), max(max(a[8 * g + 4], a[8 * g + 5]), max(a[8 * g + 6], a[8 * g + 7])));
+                if (m > dot1) {
+                    // columns arrive in increasing index, strict > keeps the earlier one on ties
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int v = a[j], idx = idx_base + 32 * part + j;
-                    if (v > dot1 && idx < nt) {
-                        if (v > dot0) { dot1 = dot0; i1 = i0; dot0 = v; i0 = idx; }
-                        else { dot1 = v; i1 = idx; }
+                    for (int j = 8 * g; j < 8 * g + 8; j++) {
+                        const int v = a[j], idx = idx_base + 32 * part + j;
+                        if (v > dot1 && idx < nt) {
+                            if (v > dot0) { dot1 = dot0; i1 = i0; dot0 = v; i0 = idx; }
+                            else { dot1 = v; i1 = idx; }
+                        }
                     }
                 }
             }
