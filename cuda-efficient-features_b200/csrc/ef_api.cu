@@ -149,7 +149,7 @@ struct ef_handle {
     // overlap the kernels of chunk c)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_cnt;
-    int host_chunk = 2;
+    int host_chunk = 4;
 
     // optional per-stage timing (bench.py): events recorded between the stages
     bool timing = false;
@@ -727,17 +727,22 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     // Chunked pipeline over three streams: the upload of chunk c+1 (getInputMat, cuda_efficient_features.cpp:71-77) and the
     // download of chunk c-1 (:316-320) overlap the kernels of chunk c.  Chunks reuse workspace slots [0, chunk): their
     // kernels are serialised on the caller's stream; outputs land in per-frame staging buffers.
+    // chunk plan: a ONE-frame head chunk (the kernels start after 8 MB instead of a whole chunk of uploads), then host_chunk frames each
     const int chunk = std::max(1, std::min(h->host_chunk, nframes));
-    const int nchunks = ef_div_up(nframes, chunk);
+    std::vector<std::pair<int, int>> plan;   // (first frame, frames)
+    if (nframes > chunk && chunk > 1) plan.emplace_back(0, 1);
+    for (int f = plan.empty() ? 0 : 1; f < nframes; f += chunk) plan.emplace_back(f, std::min(chunk, nframes - f));
+    const int nchunks = (int)plan.size();
+    if ((int)h->ev_in.size() < nchunks || (int)h->ev_cnt.size() < nchunks) return fail(h, EF_ERR_CAPACITY, "internal: chunk events");
     EF_CUDA(h, cudaEventRecord(h->ev_in[0], s));          // order the uploads after earlier work on the caller's stream
     EF_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0));
     for (int c = 0; c < nchunks; c++) {
-        for (int f = c * chunk; f < std::min(nframes, (c + 1) * chunk); f++)
+        for (int f = plan[c].first; f < plan[c].first + plan[c].second; f++)
             EF_CUDA(h, cudaMemcpy2DAsync(h->d_in + f * h->in_stride, h->in_pitch, h_imgs + f * img_stride, pitch, width, height, cudaMemcpyHostToDevice, h->s_in));
         EF_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
     }
     for (int c = 0; c < nchunks; c++) {
-        const int f0 = c * chunk, n = std::min(nframes, f0 + chunk) - f0;
+        const int f0 = plan[c].first, n = plan[c].second;
         EF_CUDA(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
         int rc = ef_detect_and_compute_batch_async(h, n, h->d_in + f0 * h->in_stride, h->in_stride, h->in_pitch, width, height,
                                                    (float*)((uint8_t*)h->d_out_kpts + f0 * h->out_kpts_stride), h->out_kpts_stride, h->out_kpts_pitch,
@@ -750,7 +755,7 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     for (int c = 0; c < nchunks; c++) {
         // one host wait per chunk to size the outputs (the reference blocks 16 times per frame); later chunks keep running
         EF_CUDA(h, cudaEventSynchronize(h->ev_cnt[c]));
-        for (int f = c * chunk; f < std::min(nframes, (c + 1) * chunk); f++) {
+        for (int f = plan[c].first; f < plan[c].first + plan[c].second; f++) {
             const int n = h->h_counts_pinned[f];
             h_counts[f] = n;
             if (n <= 0) continue;
