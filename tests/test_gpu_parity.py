@@ -396,3 +396,27 @@ def test_projection_paths_agree(torch_cuda, dtype_name):
         assert np.array_equal(imma, ref), f"{name}: mma.sync path differs from fp64 in {(imma != ref).any(axis=1).sum()} rows"
         assert np.array_equal(tc, ref), f"{name}: tcgen05 path differs from fp64 in {(tc != ref).any(axis=1).sum()} rows"
         assert np.array_equal(ef.debugProject(d, 0).cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: compute-only, BAD512 + HashSIFT512 on 40 000 precomputed keypoints at 4K
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype_name", ["BAD_512", "HASH_SIFT_512"])
+def test_compute_only_40k_keypoints_4k(torch_cuda, oracle, dtype_name):
+    import efb200, efo
+    torch = torch_cuda
+    w, h, n = 3840, 2160, 40000
+    img = oracle.synth_frame(util.SEED + 51, 0, w, h)
+    det = make_ef(nfeatures=n, dtype=efb200.BAD_256, max_width=w, max_height=h)
+    kd = det.detect(torch.from_numpy(img).cuda())                      # ~30 000 detector keypoints (sizes 31 * scale, IC angles)
+    k = np.stack([kd["x"], kd["y"], kd["size"], kd["angle"]], axis=1).astype(np.float32)
+    k = np.concatenate([k, efo.stress_keypoints(w, h, n - len(k), seed=9)])   # + border band, special angles, sizes 31..111
+    assert len(k) == n
+    if dtype_name == "BAD_512":
+        g = efb200.BAD.create(1.0, 100, max_width=w, max_height=h, max_keypoints=n).compute(img, k)
+        o = oracle.bad(img, k, 1.0, 512)
+    else:
+        g = efb200.HashSIFT.create(1.0, 100, max_width=w, max_height=h, max_keypoints=n).compute(img, k)   # default path: tcgen05 projection
+        o = oracle.hashsift(img, k, 1.0, 512)
+    assert g.shape == (n, 64)
+    assert np.array_equal(g, o), f"{(g != o).any(axis=1).sum()} of {n} descriptors differ"
