@@ -727,11 +727,15 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     // Chunked pipeline over three streams: the upload of chunk c+1 (getInputMat, cuda_efficient_features.cpp:71-77) and the
     // download of chunk c-1 (:316-320) overlap the kernels of chunk c.  Chunks reuse workspace slots [0, chunk): their
     // kernels are serialised on the caller's stream; outputs land in per-frame staging buffers.
-    // chunk plan: a ONE-frame head chunk (the kernels start after 8 MB instead of a whole chunk of uploads), then host_chunk frames each
+    // chunk plan: a ONE-frame head chunk (the kernels start after 8 MB instead of a whole chunk of uploads), host_chunk frames each,
     const int chunk = std::max(1, std::min(h->host_chunk, nframes));
     std::vector<std::pair<int, int>> plan;   // (first frame, frames)
-    if (nframes > chunk && chunk > 1) plan.emplace_back(0, 1);
-    for (int f = plan.empty() ? 0 : 1; f < nframes; f += chunk) plan.emplace_back(f, std::min(chunk, nframes - f));
+    // and a ONE-frame tail chunk (only 2.5 MB of results are still to be downloaded when the last kernel ends)
+    const bool ends = nframes > chunk + 1 && chunk > 1;
+    if (ends) plan.emplace_back(0, 1);
+    const int body_end = ends ? nframes - 1 : nframes;
+    for (int f = ends ? 1 : 0; f < body_end; f += chunk) plan.emplace_back(f, std::min(chunk, body_end - f));
+    if (ends) plan.emplace_back(nframes - 1, 1);
     const int nchunks = (int)plan.size();
     if ((int)h->ev_in.size() < nchunks || (int)h->ev_cnt.size() < nchunks) return fail(h, EF_ERR_CAPACITY, "internal: chunk events");
     EF_CUDA(h, cudaEventRecord(h->ev_in[0], s));          // order the uploads after earlier work on the caller's stream
