@@ -204,7 +204,6 @@ def main():
     launches = ef.kernelLaunchCount() - launches0
     stage_ms, ncalls = ef.stageTimes()
     ef.stageTimingEnable(False)
-    clocks = sampler.finish() if sampler else None
     nk = int(counts.sum().item())
     t = torch.tensor([ms, float(nk)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -239,6 +238,8 @@ def main():
         dt = float(tt[0].item())
         e2e = {"value": world * B * args.steps * W * H / dt / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": B * H * W,
                "d2h_bytes_per_step": int(sum(cnt)) * (20 + dbytes) + 4 * B, "ms_per_step": 1e3 * dt / args.steps}
+
+    clocks = sampler.finish() if sampler else None   # sampled through both timed regions (device-resident and host-buffer)
 
     if rank != 0:
         if world > 1:
