@@ -439,7 +439,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
     const NmsGeom ng = nms_geometry(p.nonmax_radius);
     P.fast_threshold = p.fast_threshold; P.nms_r2 = ng.r2; P.nms_R = ng.R; P.nms_block = ng.block; P.nms_K = ng.K;
     P.nfeatures = p.nfeatures;
-    P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0;
+    P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0; P.desc_by_band = 0;
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
     P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
     P.counters = h->d_counters;
@@ -454,6 +454,13 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
         ef_band_tile_rows(L.tiles_y, shard_i, shard_n, ef_div_up(ng.K * ng.block, EF_TILE), &L.own_ty0, &L.own_rows, &L.score_ty0, &L.score_rows);
         L.blk_w = ng.block ? ef_div_up(L.w, ng.block) : 0; L.blk_h = ng.block ? ef_div_up(L.h, ng.block) : 0;
         L.blur_tiles_x = ef_div_up(L.w, 64);
+        L.blur_ty0 = 0; L.blur_rows = ef_div_up(L.h, 64);
+        if (shard_n > 1) {
+            // band-sharded frame: only the rows the descriptor windows of the owned keypoints can touch (k.y +- 24)
+            const int y_lo = std::max(0, L.own_ty0 * EF_TILE - 24), y_hi = std::min(L.h, (L.own_ty0 + L.own_rows) * EF_TILE + 24);
+            L.blur_ty0 = y_lo / 64;
+            L.blur_rows = L.own_rows > 0 ? ef_div_up(y_hi, 64) - L.blur_ty0 : 0;
+        }
         L.quota = g.quota[l];
         L.surv_cap = (int)surv_capacity(L.w, L.h, ng.r2);
         L.scale = g.scale[l];
@@ -471,7 +478,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
             bands += L.own_rows;
             kblocks += ef_div_up(std::min(L.quota, p.nfeatures), 8);
             sblocks += ef_div_up(std::min(L.quota, p.nfeatures), 4);
-            btiles += L.blur_tiles_x * ef_div_up(L.h, 64);
+            btiles += L.blur_tiles_x * L.blur_rows;
         }
     }
     P.total_tiles = tiles; P.total_blur_tiles = btiles; P.total_bands = bands; P.total_kpt_blocks = kblocks; P.total_sift_blocks = sblocks; P.total_strips = strips;
@@ -842,8 +849,9 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
     ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);// every GPU writes the full keypoint matrix (identical everywhere)
     if (d_desc) {
         ef_launch_blur(P, s);     mark(h, EF_STAGE_BLUR, s);
-        // descriptor CTAs are dealt round-robin; rows of other GPUs stay zero: MAX all-reduce assembles the matrix
-        P.shard_i = shard; P.shard_n = nshards;
+        // every GPU describes the keypoints of its own band (their windows lie in the rows it blurred); rows of other GPUs stay
+        // zero: MAX all-reduce assembles the matrix
+        P.desc_by_band = nshards > 1 ? 1 : 0;
         for (int f = 0; f < nframes; f++)
             EF_CUDA(h, cudaMemset2DAsync(d_desc + f * desc_stride, desc_pitch, 0, (size_t)db, (size_t)h->prm.nfeatures, s));
         const int v = (db == 32) ? 0 : 1;

@@ -41,6 +41,7 @@ struct EfLevel {
     int tile_start;     // first tile index of this level in the all-level tile table
     int strips_x, strip_start; // NMS strips of 4 tiles per tile row; first strip index of this level
     int blur_tile_start, blur_tiles_x; // 64x64 blur tiles
+    int blur_ty0, blur_rows;           // blur tile rows of this call (whole level; band-sharded frames: the rows the owned keypoints' windows touch)
     int band_start;     // first 32-row band index of this level
     int quota;          // nfeaturesPerLevel_[s]
     int surv_cap;       // capacity of the survivor list
@@ -60,7 +61,8 @@ struct EfPipe {
     int total_tiles, total_blur_tiles, total_bands, total_kpt_blocks, total_sift_blocks, total_strips;
     int nfeatures;              // output capacity (columns)
     int desc_type, desc_bytes;
-    int shard_i, shard_n;       // descriptor CTAs are dealt round-robin to shard_n GPUs (ef_band_finish_async); 0, 1 otherwise
+    int shard_i, shard_n;       // descriptor CTAs dealt round-robin to shard_n GPUs (unused by ef_band_*: kept for callers that shard by CTA); 0, 1 otherwise
+    int desc_by_band;           // ef_band_finish_async: describe only the keypoints whose tile row lies in [own_ty0, own_ty0 + own_rows)
     int select_from_counters;   // select stage: candidate count comes from counters[].overflow (merged band candidates), not from rowcnt
     // caller buffers (frame f at base + f*stride)
     const uint8_t* img0; unsigned long long img0_stride; int img0_pitch;

@@ -995,8 +995,8 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::blur_tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.blur_tile_start;
-    const int tyi = t / L.blur_tiles_x;
-    const int x0 = (t - tyi * L.blur_tiles_x) * BL_TW, y0 = tyi * BL_TH;
+    const int tyl = t / L.blur_tiles_x, tyi = tyl + L.blur_ty0;
+    const int x0 = (t - tyl * L.blur_tiles_x) * BL_TW, y0 = tyi * BL_TH;
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
     const bool fast = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0 && x0 >= 4 && x0 + BL_TW + 4 <= L.w;
@@ -1132,9 +1132,9 @@ __global__ void __launch_bounds__(256) ef_band_merge_kernel(const __grid_constan
     }
 }
 
-// zero the descriptor rows whose HashSIFT feature CTA belongs to another GPU (their SIFT vectors were not computed here),
-// so that an element-wise MAX all-reduce of the descriptor matrices assembles the frame's descriptors
-__global__ void __launch_bounds__(256) ef_band_mask_rows_kernel(const __grid_constant__ EfPipe p, int hashsift)
+// zero the descriptor rows of keypoints owned by another band (the projection ran over all rows; their SIFT vectors were not
+// computed here), so that an element-wise MAX all-reduce of the descriptor matrices assembles the frame's descriptors
+__global__ void __launch_bounds__(256) ef_band_mask_rows_kernel(const __grid_constant__ EfPipe p)
 {
     const int frame = blockIdx.y;
     const int chunks = p.desc_bytes / 16;
@@ -1144,9 +1144,9 @@ __global__ void __launch_bounds__(256) ef_band_mask_rows_kernel(const __grid_con
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
     int level = p.first_level, offset = 0;
     while (level + 1 < p.nlevels && row >= offset + ctr[level].selected) { offset += ctr[level].selected; level++; }
-    const int blk = hashsift ? p.lv[level].sift_block_start + (row - offset) / 4      // EF_SIFT_KP_PER_CTA (ef_hashsift.cu)
-                             : p.lv[level].kpt_block_start + (row - offset) / 8;      // EF_DESC_WARPS (ef_desc.cu)
-    if (blk % p.shard_n == p.shard_i) return;
+    const EfLevel& L = p.lv[level];
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[row - offset];
+    if ((unsigned)((k.y >> 5) - L.own_ty0) < (unsigned)L.own_rows) return;      // owned: keep
     uint8_t* d = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch + 16 * ch;
     if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
     else for (int i = 0; i < 16; i++) d[i] = 0;
@@ -1165,6 +1165,7 @@ void ef_launch_band_merge(const EfPipe& p, const uint8_t* all, unsigned long lon
 void ef_launch_band_mask_rows(const EfPipe& p, bool hashsift, cudaStream_t s)
 {
     const int threads = p.nfeatures * (p.desc_bytes / 16);
-    ef_band_mask_rows_kernel<<<dim3(ef_div_up(threads, 256), p.nframes), 256, 0, s>>>(p, hashsift ? 1 : 0);
+    (void)hashsift;
+    ef_band_mask_rows_kernel<<<dim3(ef_div_up(threads, 256), p.nframes), 256, 0, s>>>(p);
     EF_COUNT_LAUNCH(1);
 }
