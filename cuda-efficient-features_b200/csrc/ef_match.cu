@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) ef_match_ratio_cross_kernel(const int* __
 // tcgen05 path (ef_match_tc.cu)
 size_t ef_match_tc_expanded_bytes(int n, int desc_bytes);
 int ef_match_tc_splits(int nq, int nt);
-void ef_match_tc_expand(const uint8_t* d_desc, size_t pitch, int n, int desc_bytes, uint8_t* d_out, cudaStream_t s);
+void ef_match_tc_expand(const uint8_t* d_desc, size_t pitch, int n, int desc_bytes, bool role_b, uint8_t* d_out, cudaStream_t s);
 void ef_match_tc_knn(const uint8_t* qexp, int nq, const uint8_t* texp, int nt, int desc_bytes, int k, int4* d_partial, int* d_idx, int* d_dist, cudaStream_t s);
 
 namespace {
@@ -204,7 +204,7 @@ bool match_use_tc(int nq, int nt)
 }
 
 // scratch layout: [partial lists][index/distance rows of the cross check][+-1 expansion of the query set][of the train set]
-struct MatchScratch { size_t partial, rows, qexp, texp, total; };
+struct MatchScratch { size_t partial, rows, qexp, texp, qexp_b, texp_a, total; };   // *_b / *_a: the other role's operand order (cross check)
 MatchScratch match_scratch(int nq, int nt)
 {
     MatchScratch m{};
@@ -215,7 +215,9 @@ MatchScratch match_scratch(int nq, int nt)
     m.rows = ef_align_up(std::max(alu, tc), 256);
     m.qexp = m.rows + ef_align_up(4 * mx * sizeof(int), 256);
     m.texp = m.qexp + ef_match_tc_expanded_bytes(nq, 64);
-    m.total = m.texp + ef_match_tc_expanded_bytes(nt, 64) + 256;
+    m.qexp_b = m.texp + ef_match_tc_expanded_bytes(nt, 64);
+    m.texp_a = m.qexp_b + ef_match_tc_expanded_bytes(nq, 64);
+    m.total = m.texp_a + ef_match_tc_expanded_bytes(nt, 64) + 256;
     return m;
 }
 
@@ -270,8 +272,8 @@ int ef_match_knn_async(const uint8_t* d_query, size_t qpitch, int nq, const uint
     uint8_t* sc = reinterpret_cast<uint8_t*>(d_scratch);
     if (!match_use_tc(nq, nt)) return knn_launch_alu(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, k, d_idx, d_dist, sc, s);
     const MatchScratch m = match_scratch(nq, nt);
-    ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, sc + m.qexp, s);
-    ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, sc + m.texp, s);
+    ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, false, sc + m.qexp, s);
+    ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, true, sc + m.texp, s);
     ef_match_tc_knn(sc + m.qexp, nq, sc + m.texp, nt, desc_bytes, k, reinterpret_cast<int4*>(sc + m.partial), d_idx, d_dist, s);
     return cudaGetLastError() == cudaSuccess ? EF_OK : match_fail(EF_ERR_CUDA, "kernel launch failed");
 }
@@ -291,10 +293,12 @@ int ef_match_cross_check_async(const uint8_t* d_query, size_t qpitch, int nq, co
     int* rows = reinterpret_cast<int*>(sc + m.rows);
     int *fwd_idx = rows, *fwd_dist = rows + mx, *bwd_idx = rows + 2 * mx, *bwd_dist = rows + 3 * mx;
     if (match_use_tc(nq, nt)) {
-        ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, sc + m.qexp, s);
-        ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, sc + m.texp, s);
+        ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, false, sc + m.qexp, s);
+        ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, true, sc + m.texp, s);
+        ef_match_tc_expand(d_query, qpitch, nq, desc_bytes, true, sc + m.qexp_b, s);
+        ef_match_tc_expand(d_train, tpitch, nt, desc_bytes, false, sc + m.texp_a, s);
         ef_match_tc_knn(sc + m.qexp, nq, sc + m.texp, nt, desc_bytes, 1, reinterpret_cast<int4*>(sc + m.partial), fwd_idx, fwd_dist, s);
-        ef_match_tc_knn(sc + m.texp, nt, sc + m.qexp, nq, desc_bytes, 1, reinterpret_cast<int4*>(sc + m.partial), bwd_idx, bwd_dist, s);
+        ef_match_tc_knn(sc + m.texp_a, nt, sc + m.qexp_b, nq, desc_bytes, 1, reinterpret_cast<int4*>(sc + m.partial), bwd_idx, bwd_dist, s);
     } else {
         rc = knn_launch_alu(d_query, qpitch, nq, d_train, tpitch, nt, desc_bytes, 1, fwd_idx, fwd_dist, sc + m.partial, s);
         if (rc != EF_OK) return rc;
