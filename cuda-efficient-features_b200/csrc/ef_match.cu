@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256) ef_match_ratio_cross_kernel(const int* __
 // tcgen05 path (ef_match_tc.cu)
 size_t ef_match_tc_expanded_bytes(int n, int desc_bytes);
 int ef_match_tc_splits(int nq, int nt);
+int ef_match_tc_max_lists(void);
 void ef_match_tc_expand(const uint8_t* d_desc, size_t pitch, int n, int desc_bytes, bool role_b, uint8_t* d_out, cudaStream_t s);
 void ef_match_tc_knn(const uint8_t* qexp, int nq, const uint8_t* texp, int nt, int desc_bytes, int k, int4* d_partial, int* d_idx, int* d_dist, cudaStream_t s);
 
@@ -210,7 +211,7 @@ MatchScratch match_scratch(int nq, int nt)
     MatchScratch m{};
     const size_t mx = (size_t)std::max(std::max(nq, nt), 1);
     const size_t alu = (size_t)std::max(match_splits(nq, nt) * (size_t)nq, match_splits(nt, nq) * (size_t)nt) * sizeof(int4);
-    const size_t tc = (size_t)std::max(2 * ef_match_tc_splits(nq, nt) * (size_t)nq, 2 * ef_match_tc_splits(nt, nq) * (size_t)nt) * sizeof(int4);
+    const size_t tc = (size_t)ef_match_tc_max_lists() * mx * sizeof(int4);
     m.partial = 0;
     m.rows = ef_align_up(std::max(alu, tc), 256);
     m.qexp = m.rows + ef_align_up(4 * mx * sizeof(int), 256);
