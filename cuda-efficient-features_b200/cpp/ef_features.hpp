@@ -191,4 +191,52 @@ private:
     using Describer::Describer;
 };
 
+// cv::BFMatcher for NORM_HAMMING over descriptors that stay on the device (callers: samples/sample_image_sequence.cpp:81,115-137,
+// samples/sample_feature_matching.cpp:99-101).  All buffers are the caller's (cv::cuda::GpuMat in an OpenCV build):
+//   knnMatchAsync: idx / dist = nq x k CV_32S (k = 1 or 2), row q = the k nearest train rows in OpenCV's order, -1 where missing
+//   matchAsync   : trainIdx / dist = nq CV_32S; with crossCheck, trainIdx is -1 for the queries OpenCV would omit
+//   scratch      : scratchBytes(nq, nt) bytes, 16-byte aligned
+class BFMatcher
+{
+public:
+    explicit BFMatcher(int normType = 6 /* NORM_HAMMING */, bool crossCheck = false) : crossCheck_(crossCheck)
+    {
+        if (normType != 6) throw Error(EF_ERR_UNSUPPORTED, "only NORM_HAMMING (defaultNorm() of the path's descriptors) is implemented");
+    }
+    static std::unique_ptr<BFMatcher> create(int normType = 6, bool crossCheck = false) { return std::unique_ptr<BFMatcher>(new BFMatcher(normType, crossCheck)); }
+    static size_t scratchBytes(int nq, int nt) { return ef_match_scratch_bytes(nq, nt); }
+
+    void knnMatchAsync(const MatView& query, const MatView& train, int k, int* d_idx, int* d_dist, void* d_scratch, void* stream = nullptr) const
+    {
+        check(ef_match_knn_async(static_cast<const uint8_t*>(query.data), query.step, query.rows, static_cast<const uint8_t*>(train.data), train.step,
+                                 train.rows, query.cols, k, d_idx, d_dist, d_scratch, stream));
+    }
+    void matchAsync(const MatView& query, const MatView& train, int* d_trainIdx, int* d_dist, void* d_scratch, void* stream = nullptr) const
+    {
+        if (crossCheck_)
+            check(ef_match_cross_check_async(static_cast<const uint8_t*>(query.data), query.step, query.rows, static_cast<const uint8_t*>(train.data),
+                                             train.step, train.rows, query.cols, d_trainIdx, d_dist, d_scratch, stream));
+        else knnMatchAsync(query, train, 1, d_trainIdx, d_dist, d_scratch, stream);
+    }
+    // the ratio + cross-check loop of samples/sample_image_sequence.cpp:121-137 over two k = 2 results: d_out[q] = train row or -1
+    static void ratioCrossFilterAsync(const int* d_idx12, const int* d_dist12, int nq, const int* d_idx21, const int* d_dist21, int nt,
+                                      double uniqueness, int* d_out, void* stream = nullptr)
+    {
+        check(ef_match_ratio_cross_async(d_idx12, d_dist12, nq, d_idx21, d_dist21, nt, uniqueness, d_out, stream));
+    }
+
+private:
+    static void check(int rc) { if (rc != EF_OK) throw Error(rc, ef_match_last_error_string()); }
+    bool crossCheck_;
+};
+
+// convertToGray (samples/sample_common.cpp:35-45) on the device: 8UC3 (BGR) / 8UC4 (BGRA) -> 8UC1; 8UC1 passes through
+inline void convertToGrayAsync(const MatView& src, int channels, const MatView& dstGray, void* stream = nullptr)
+{
+    if (channels == 1) throw Error(EF_ERR_BAD_ARG, "8UC1 input needs no conversion: use it as is");
+    const int rc = ef_bgr_to_gray_async(static_cast<const uint8_t*>(src.data), src.step, src.cols, src.rows, channels,
+                                        static_cast<uint8_t*>(dstGray.data), dstGray.step, stream);
+    if (rc != EF_OK) throw Error(rc, "Image should be 8UC1, 8UC3 or 8UC4");   // CV_Error(StsBadArg, ...), sample_common.cpp:44
+}
+
 } // namespace efb200
