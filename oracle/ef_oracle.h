@@ -14,9 +14,14 @@
  *                 detector (cuda_fast.cu, cuda_efficient_features.cu, cuda_efficient_features.cpp)
  *                 with the deterministic rules of DESIGN.md (no candidate cap, raster output
  *                 order, total order for top-K ties) and the FMA contraction pattern nvcc emits
- *                 for the reference source.  PARITY UNPINNED for the detector and for the two
- *                 OpenCV-CUDA library calls it depends on (cv::cuda::resize, Gaussian filter):
- *                 neither can be run here (no OpenCV-CUDA, no reference tests for these stages).
+ *                 for the reference source.  PINNED on the GPU box for FAST-9, the Harris response
+ *                 (bit for bit), the radius NMS, limitPoints and scalePoints, and to <= 2 ulp for the IC
+ *                 angle (the reference calls CUDA atan2f): tests/test_gpu_reference_kernels.py runs the
+ *                 reference's own cuda_fast.cu / cuda_efficient_features.cu, compiled unmodified into
+ *                 oracle/_ref/libef_ref_cuda.so against oracle/shim_cuda/, next to this restatement and
+ *                 the product kernels.  PARITY UNPINNED remains for the two OpenCV-CUDA library calls the
+ *                 detector depends on (cv::cuda::resize, Gaussian filter): third-party, not vendored, and
+ *                 no reference test covers them.
  */
 #ifndef EF_ORACLE_H
 #define EF_ORACLE_H

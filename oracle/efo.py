@@ -265,6 +265,62 @@ class Reference:
         return resp
 
 
+REF_CUDA_SO = REF_SO.parent / "libef_ref_cuda.so"
+
+
+class ReferenceCuda:
+    """The reference's own CUDA detector kernels (cuda_fast.cu, cuda_efficient_features.cu, UNMODIFIED), built by oracle/Makefile
+    (target ref_cuda) into oracle/_ref/libef_ref_cuda.so against oracle/shim_cuda.  Needs a GPU: `-m gpu` tests only."""
+
+    def __init__(self):
+        if not REF_CUDA_SO.exists():
+            raise FileNotFoundError(f"{REF_CUDA_SO} not built (needs /root/reference and nvcc; run make -C oracle ref_cuda)")
+        L = C.CDLL(str(REF_CUDA_SO))
+        self.L = L
+        sp = C.POINTER(C.c_short)
+        L.efrefcu_fast.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, sp]
+        L.efrefcu_responses_angles.argtypes = [_u8p, C.c_int, C.c_int, sp, C.c_int, _f32p, _f32p]
+        L.efrefcu_responses_angles.restype = None
+        L.efrefcu_nms_limit.argtypes = [sp, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, sp, _f32p]
+        L.efrefcu_scale.argtypes = [sp, C.c_int, C.c_float, C.c_int, sp, C.POINTER(C.c_int), _f32p]
+        L.efrefcu_scale.restype = None
+
+    @staticmethod
+    def available() -> bool:
+        return REF_CUDA_SO.exists()
+
+    def fast(self, img, threshold=20, border=15, maxpoints=None):
+        """createMask + calcKeypoints: n x 2 int16 (x, y) in the kernel's atomic arrival order"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = int(maxpoints if maxpoints is not None else w * h)
+        xy = np.zeros((cap, 2), np.int16)
+        n = self.L.efrefcu_fast(_p(img, _u8p), w, h, threshold, border, cap, _p(xy, C.POINTER(C.c_short)))
+        return xy[:n].copy()
+
+    def responses_angles(self, img, xy):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        xy = np.ascontiguousarray(xy, np.int16)
+        r = np.zeros(len(xy), np.float32); a = np.zeros(len(xy), np.float32)
+        self.L.efrefcu_responses_angles(_p(img, _u8p), w, h, _p(xy, C.POINTER(C.c_short)), len(xy), _p(r, _f32p), _p(a, _f32p))
+        return r, a
+
+    def nms_limit(self, xy, resp, w, h, radius=15.0, maxpoints=-1):
+        xy = np.ascontiguousarray(xy, np.int16); resp = np.ascontiguousarray(resp, np.float32)
+        oxy = np.zeros((max(len(xy), 1), 2), np.int16); orr = np.zeros(max(len(xy), 1), np.float32)
+        m = self.L.efrefcu_nms_limit(_p(xy, C.POINTER(C.c_short)), _p(resp, _f32p), len(xy), w, h, float(radius), int(maxpoints),
+                                     _p(oxy, C.POINTER(C.c_short)), _p(orr, _f32p))
+        return oxy[:m].copy(), orr[:m].copy()
+
+    def scale(self, xy, scale, octave):
+        xy = np.ascontiguousarray(xy, np.int16)
+        oxy = np.zeros_like(xy); oc = np.zeros(len(xy), np.int32); sz = np.zeros(len(xy), np.float32)
+        self.L.efrefcu_scale(_p(xy, C.POINTER(C.c_short)), len(xy), float(scale), int(octave), _p(oxy, C.POINTER(C.c_short)),
+                             _p(oc, C.POINTER(C.c_int)), _p(sz, _f32p))
+        return oxy, oc, sz
+
+
 def stress_keypoints(w: int, h: int, n: int, seed: int = 1) -> np.ndarray:
     """Keypoint stress set: uniform positions including the border band,
     special angles, sizes 31..111.  Returns n x 4 float32 (x, y, size, angle)."""

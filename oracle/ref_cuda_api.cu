@@ -1,0 +1,101 @@
+// ref_cuda_api.cu -- TEST INFRASTRUCTURE: C entry points over the reference's own CUDA detector kernels, compiled UNMODIFIED from
+// /root/reference/modules/cuda_efficient_features/src/{cuda_fast.cu, cuda_efficient_features.cu} against oracle/shim_cuda (default nvcc
+// flags = the reference's build, modules/cuda_efficient_features/CMakeLists.txt:22-29: contraction on).  Used by tests/ only, to pin the
+// CPU restatement of the detector (oracle/ef_oracle.c) and the product kernels against what the reference really computes:
+// FAST-9 corner set, Harris responses, radius NMS, limitPoints, IC angles, scalePoints.
+#include <cstdint>
+#include <cstring>
+
+#include <cuda_fast.cu>                    // -I<reference>/modules/cuda_efficient_features/src
+#include <cuda_efficient_features.cu>
+
+using namespace cv;
+using namespace cv::cuda;
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { cudaMalloc(&p, bytes ? bytes : 16); cudaMemset(p, 0, bytes ? bytes : 16); }
+    ~DevBuf() { cudaFree(p); }
+};
+}
+
+extern "C" {
+
+// createMask (cuda_efficient_features.cpp:176-182) + calcKeypoints (cuda_fast.cu:224-246).  Returns the number of corners found
+// (capped at maxpoints like the reference); xy = maxpoints x 2 shorts.
+int efrefcu_fast(const uint8_t* h_img, int w, int h, int threshold, int border, int maxpoints, short* h_xy)
+{
+    DevBuf img((size_t)w * h), mask((size_t)w * h), kp(sizeof(float) * 4 * (size_t)maxpoints), cnt(16);
+    unsigned int* h_cnt = nullptr;
+    cudaMallocHost((void**)&h_cnt, 16);
+    cudaMemcpy(img.p, h_img, (size_t)w * h, cudaMemcpyHostToDevice);
+    {
+        std::vector<uint8_t> m((size_t)w * h, 0);
+        for (int y = border; y < h - border; y++) std::memset(&m[(size_t)y * w + border], 255, (size_t)std::max(0, w - 2 * border));
+        cudaMemcpy(mask.p, m.data(), m.size(), cudaMemcpyHostToDevice);
+    }
+    GpuMat gimg(h, w, CV_8UC1, img.p, (size_t)w), gmask(h, w, CV_8UC1, mask.p, (size_t)w);
+    GpuMat gkp(4, maxpoints, CV_32F, kp.p, sizeof(float) * (size_t)maxpoints), gcnt(1, 4, CV_32S, cnt.p, 16);
+    HostMem hcnt(1, 4, h_cnt, 16);
+    calcKeypoints(gimg, gmask, gkp, maxpoints, threshold, gcnt, hcnt, 0);
+    const int n = gkp.cols;
+    cudaMemcpy(h_xy, kp.p, sizeof(short) * 2 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFreeHost(h_cnt);
+    return n;
+}
+
+// calcResponses (:360-374) and calcAngles (:376-390) on given points (n x 2 shorts)
+void efrefcu_responses_angles(const uint8_t* h_img, int w, int h, const short* h_xy, int n, float* h_resp, float* h_angle)
+{
+    if (n <= 0) return;
+    DevBuf img((size_t)w * h), pts(sizeof(float) * 5 * (size_t)n);
+    cudaMemcpy(img.p, h_img, (size_t)w * h, cudaMemcpyHostToDevice);
+    cudaMemcpy(pts.p, h_xy, sizeof(short) * 2 * (size_t)n, cudaMemcpyHostToDevice);
+    GpuMat gimg(h, w, CV_8UC1, img.p, (size_t)w), gp(5, n, CV_32F, pts.p, sizeof(float) * (size_t)n);
+    calcResponses(gimg, gp, 0);
+    calcAngles(gimg, gp, 0);
+    cudaDeviceSynchronize();
+    if (h_resp) cudaMemcpy(h_resp, gp.ptr<float>(1), sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+    if (h_angle) cudaMemcpy(h_angle, gp.ptr<float>(2), sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+}
+
+// radiusSuppression (:281-342) then, if maxpoints >= 0, limitPoints (:344-358).  In: n points + responses; out: survivors.
+int efrefcu_nms_limit(const short* h_xy, const float* h_resp, int n, int w, int h, float radius, int maxpoints, short* o_xy, float* o_resp)
+{
+    if (n <= 0) return 0;
+    DevBuf src(sizeof(float) * 5 * (size_t)n), dst(sizeof(float) * 5 * (size_t)n);
+    const int bufInts = radiusSuppressionBufferSize(Size(w, h), n);
+    DevBuf buf(sizeof(int) * (size_t)bufInts);
+    int* h_cnt = nullptr;
+    cudaMallocHost((void**)&h_cnt, 16);
+    cudaMemcpy(src.p, h_xy, sizeof(short) * 2 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy((char*)src.p + sizeof(float) * (size_t)n, h_resp, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice);
+    GpuMat gsrc(5, n, CV_32F, src.p, sizeof(float) * (size_t)n), gdst(5, n, CV_32F, dst.p, sizeof(float) * (size_t)n);
+    GpuMat gbuf(1, bufInts, CV_32S, buf.p, sizeof(int) * (size_t)bufInts);
+    HostMem hcnt(1, 4, h_cnt, 16);
+    radiusSuppression(gsrc, gdst, Size(w, h), radius, gbuf, hcnt, 0);
+    if (maxpoints >= 0) limitPoints(gdst, maxpoints, 0);
+    cudaDeviceSynchronize();
+    const int m = gdst.cols;
+    cudaMemcpy(o_xy, gdst.ptr<short2>(0), sizeof(short) * 2 * (size_t)m, cudaMemcpyDeviceToHost);
+    cudaMemcpy(o_resp, gdst.ptr<float>(1), sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost);
+    cudaFreeHost(h_cnt);
+    return m;
+}
+
+// scalePoints (:392-407): in-place on n points; returns scaled xy, octave and size rows
+void efrefcu_scale(const short* h_xy, int n, float scale, int octave, short* o_xy, int* o_octave, float* o_size)
+{
+    if (n <= 0) return;
+    DevBuf pts(sizeof(float) * 5 * (size_t)n);
+    cudaMemcpy(pts.p, h_xy, sizeof(short) * 2 * (size_t)n, cudaMemcpyHostToDevice);
+    GpuMat gp(5, n, CV_32F, pts.p, sizeof(float) * (size_t)n);
+    scalePoints(gp, scale, octave, 0);
+    cudaDeviceSynchronize();
+    cudaMemcpy(o_xy, gp.ptr<short2>(0), sizeof(short) * 2 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(o_octave, gp.ptr<int>(3), sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(o_size, gp.ptr<float>(4), sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+}
+
+} // extern "C"
