@@ -284,6 +284,9 @@ class ReferenceCuda:
         L.efrefcu_nms_limit.argtypes = [sp, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, sp, _f32p]
         L.efrefcu_scale.argtypes = [sp, C.c_int, C.c_float, C.c_int, sp, C.POINTER(C.c_int), _f32p]
         L.efrefcu_scale.restype = None
+        L.efrefcu_time_detect_levels.argtypes = [C.POINTER(_u8p), C.POINTER(C.c_int), C.POINTER(C.c_int), _f32p, C.POINTER(C.c_int), C.c_int,
+                                                 C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int)]
+        L.efrefcu_time_detect_levels.restype = C.c_float
 
     @staticmethod
     def available() -> bool:
@@ -312,6 +315,17 @@ class ReferenceCuda:
         m = self.L.efrefcu_nms_limit(_p(xy, C.POINTER(C.c_short)), _p(resp, _f32p), len(xy), w, h, float(radius), int(maxpoints),
                                      _p(oxy, C.POINTER(C.c_short)), _p(orr, _f32p))
         return oxy[:m].copy(), orr[:m].copy()
+
+    def time_detect_levels(self, levels, scales, quotas, threshold=20, radius=15.0, iters=20):
+        """the reference's per-level detector sequence on its own kernels for the level images of one frame:
+        (mean ms per frame, keypoints per level)"""
+        n = len(levels)
+        imgs = [np.ascontiguousarray(a, np.uint8) for a in levels]
+        ptrs = (_u8p * n)(*[_p(a, _u8p) for a in imgs])
+        ws = (C.c_int * n)(*[a.shape[1] for a in imgs]); hs = (C.c_int * n)(*[a.shape[0] for a in imgs])
+        sc = np.ascontiguousarray(scales, np.float32); q = (C.c_int * n)(*[int(v) for v in quotas]); out = (C.c_int * n)()
+        ms = self.L.efrefcu_time_detect_levels(ptrs, ws, hs, _p(sc, _f32p), q, n, threshold, float(radius), iters, out)
+        return float(ms), [int(v) for v in out]
 
     def scale(self, xy, scale, octave):
         xy = np.ascontiguousarray(xy, np.int16)

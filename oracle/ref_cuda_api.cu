@@ -98,4 +98,66 @@ void efrefcu_scale(const short* h_xy, int n, float scale, int octave, short* o_x
     cudaMemcpy(o_size, gp.ptr<float>(4), sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
 }
 
+// The per-level detector sequence of EfficientFeaturesImpl::detectAndComputeAsync (cuda_efficient_features.cpp:244-272,310) on the
+// reference's own kernels, for the level images of ONE frame (the pyramid itself is cv::cuda::resize: third-party, not timed):
+// calcKeypoints (capacity 0.1 * area, :35,252) -> calcResponses -> radiusSuppression -> limitPoints -> calcAngles -> scalePoints.
+// Buffers are allocated once like the reference's DeviceBuffers; returns the mean milliseconds per frame over `iters` (wall clock around
+// the stream, like samples/sample_benchmark.cpp) and the keypoints of the last iteration per level in n_out.
+float efrefcu_time_detect_levels(const uint8_t* const* h_levels, const int* ws, const int* hs, const float* scales, const int* quotas, int nlevels,
+                                 int threshold, float radius, int iters, int* n_out)
+{
+    struct Lv { uint8_t *img, *mask; float *tmp, *kpts; int* buf; int maxpoints, bufInts; };
+    std::vector<Lv> lv(nlevels);
+    unsigned int* h_cnt = nullptr;
+    cudaMallocHost((void**)&h_cnt, 16);
+    for (int l = 0; l < nlevels; l++) {
+        const int w = ws[l], h = hs[l];
+        Lv& L = lv[l];
+        L.maxpoints = cvRound(0.1 * (double)w * h);
+        L.bufInts = radiusSuppressionBufferSize(Size(w, h), L.maxpoints);
+        cudaMalloc((void**)&L.img, (size_t)w * h); cudaMalloc((void**)&L.mask, (size_t)w * h);
+        cudaMalloc((void**)&L.tmp, sizeof(float) * 4 * (size_t)L.maxpoints); cudaMalloc((void**)&L.kpts, sizeof(float) * 5 * (size_t)L.maxpoints);
+        cudaMalloc((void**)&L.buf, sizeof(int) * (size_t)L.bufInts);
+        cudaMemcpy(L.img, h_levels[l], (size_t)w * h, cudaMemcpyHostToDevice);
+        std::vector<uint8_t> m((size_t)w * h, 0);
+        for (int y = 15; y < h - 15; y++) std::memset(&m[(size_t)y * w + 15], 255, (size_t)std::max(0, w - 30));
+        cudaMemcpy(L.mask, m.data(), m.size(), cudaMemcpyHostToDevice);
+    }
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    double total_ms = 0;
+    for (int it = 0; it <= iters; it++) {
+        cudaStreamSynchronize(st);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int l = 0; l < nlevels; l++) {
+            Lv& L = lv[l];
+            const int w = ws[l], h = hs[l];
+            GpuMat image(h, w, CV_8UC1, L.img, (size_t)w), mask(h, w, CV_8UC1, L.mask, (size_t)w);
+            GpuMat tmppoints(4, L.maxpoints, CV_32F, L.tmp, sizeof(float) * (size_t)L.maxpoints);
+            GpuMat keypoints(5, L.maxpoints, CV_32F, L.kpts, sizeof(float) * (size_t)L.maxpoints);
+            GpuMat d_buffer(L.bufInts, 1, CV_32S, L.buf, sizeof(int));
+            HostMem h_buffer(1, 4, h_cnt, 16);
+            calcKeypoints(image, mask, tmppoints, L.maxpoints, threshold, d_buffer, h_buffer, st);
+            calcResponses(image, tmppoints, st);
+            radiusSuppression(tmppoints, keypoints, image.size(), radius, d_buffer, h_buffer, st);
+            limitPoints(keypoints, quotas[l], st);
+            calcAngles(image, keypoints, st);
+            scalePoints(keypoints, scales[l], l, st);
+            n_out[l] = keypoints.cols;
+        }
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0) total_ms += ms;          // one discarded warm-up iteration (sample_benchmark.cpp:39-52)
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    for (Lv& L : lv) { cudaFree(L.img); cudaFree(L.mask); cudaFree(L.tmp); cudaFree(L.kpts); cudaFree(L.buf); }
+    cudaStreamDestroy(st);
+    cudaFreeHost(h_cnt);
+    return (float)(total_ms / iters);
+}
+
 } // extern "C"
