@@ -666,17 +666,20 @@ int ef_detect_and_compute_async(ef_handle* h, const uint8_t* d_img, size_t pitch
     return ef_detect_and_compute_batch_async(h, 1, d_img, 0, pitch, width, height, d_kpts, 0, kpts_pitch, d_desc, 0, desc_pitch, d_count, stream);
 }
 
+// rows_path: keypoints come from a 5 x N matrix (integer coordinates, size forced to 31)
 static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int width, int height, const float4* d_k4, int n,
-                          uint8_t* d_desc, size_t desc_pitch, cudaStream_t s)
+                          uint8_t* d_desc, size_t desc_pitch, cudaStream_t s, bool rows_path = false)
 {
     const ef_params& p = h->prm;
     EfDescJob job;
     job.img = d_img; job.w = width; job.h = height; job.pitch = (int)pitch;
     job.kpts = d_k4; job.n = n; job.scale = p.desc_scale;
     job.desc = d_desc; job.desc_pitch = (int)desc_pitch; job.nbits = desc_bytes_of(p.desc_type) * 8;
+    // integer keypoints of size 31 at scale 1 on a 16-byte aligned image: the window-staging kernels of the pipeline apply
+    job.staged31 = (rows_path && p.desc_scale == 1.f && ((reinterpret_cast<uintptr_t>(d_img) | pitch) & 15) == 0) ? 1 : 0;
     const int v = job.nbits == 256 ? 0 : 1;
     if (is_bad(p.desc_type)) {
-        ef_launch_integral(d_img, width, height, (int)pitch, h->d_integral, h->d_segsum, s);
+        if (!job.staged31) ef_launch_integral(d_img, width, height, (int)pitch, h->d_integral, h->d_segsum, s);
         EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
         ef_launch_bad_flat(job, h->d_integral, t, s);
     } else {
@@ -718,7 +721,7 @@ int ef_compute_rows_async(ef_handle* h, const uint8_t* d_img, size_t pitch, int 
     const int rc = compute_check(h, d_img, pitch, width, height, d_kpts5, n, d_desc, desc_pitch);
     if (rc != -1) return rc;
     ef_launch_convert_rows(d_kpts5, kpts_pitch, n, h->d_kpts4, (cudaStream_t)stream);
-    return compute_common(h, d_img, pitch, width, height, h->d_kpts4, n, d_desc, desc_pitch, (cudaStream_t)stream);
+    return compute_common(h, d_img, pitch, width, height, h->d_kpts4, n, d_desc, desc_pitch, (cudaStream_t)stream, true);
 }
 
 int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h_imgs, size_t img_stride, size_t pitch,

@@ -138,6 +138,8 @@ struct EfDescJob {
     float scale;             // BAD scaleFactor / HashSIFT croppingScale
     uint8_t* desc; int desc_pitch;
     int nbits;
+    int staged31;            // every keypoint has integer coordinates and size 31, scale == 1, image base and pitch 16-byte aligned:
+                             // the window-staging kernels of the detectAndCompute path apply (5 x N GpuMat compute path)
 };
 struct EfBadTables { const uchar4* boxes_xyxy; const unsigned char* radius; const float* thresholds; };
 

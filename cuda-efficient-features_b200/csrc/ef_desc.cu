@@ -220,9 +220,12 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_flat_kernel(const E
     ef_bad_describe(I, a, t, job.nbits, job.w, job.h, job.desc + (size_t)i * job.desc_pitch, lane);
 }
 
+void ef_launch_bad_flat_window(const EfDescJob& job, const EfBadTables& t, cudaStream_t s);
+
 void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const EfBadTables& t, cudaStream_t s)
 {
     if (job.n <= 0) return;
+    if (job.staged31) { ef_launch_bad_flat_window(job, t, s); return; }
     ef_bad_flat_kernel<<<ef_div_up(job.n, EF_DESC_WARPS), EF_DESC_WARPS * 32, 0, s>>>(job, integral, t);
     EF_COUNT_LAUNCH(1);
 }
@@ -239,31 +242,9 @@ void ef_launch_bad_flat(const EfDescJob& job, const unsigned* integral, const Ef
 #define EF_BW_ROWS (2 * EF_BW_HALF)     // 48 window rows
 #define EF_BW_WORDS (EF_BW_PITCH / 2)   // 33
 
-__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const __grid_constant__ EfPipe p, const EfBadTables t)
+// window integral of one keypoint (kx, ky integers) into W ((EF_BW_ROWS + 1) x EF_BW_WORDS words of shared memory), one warp
+__device__ __forceinline__ void ef_bad_window_integral(unsigned* __restrict__ W, const uint8_t* __restrict__ img, int pitch, int h, int gx0, int wy0, int lane)
 {
-    extern __shared__ __align__(16) unsigned s_win_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int frame = blockIdx.y;
-    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
-    const int bx = (int)blockIdx.x * p.shard_n + p.shard_i;   // descriptor CTAs dealt round-robin over the GPUs of a band-sharded frame
-    if (bx >= p.total_kpt_blocks) return;
-    int level = p.first_level;
-    while (level + 1 < p.nlevels && bx >= p.lv[level + 1].kpt_block_start) level++;
-    const EfLevel& L = p.lv[level];
-    const int i = (bx - L.kpt_block_start) * EF_DESC_WARPS + warp;
-    if (i >= ctr[level].selected) return;
-    int offset = 0;
-    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
-    const int row = offset + i;
-    if (row >= p.nfeatures) return;
-
-    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
-    if (p.desc_by_band && (unsigned)((k.y >> 5) - L.own_ty0) >= (unsigned)L.own_rows) return;   // another band's keypoint (warp-uniform)
-    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
-    const int pitch = L.blur_pitch;
-    unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);
-    const int gx0 = (k.x - EF_BW_HALF) & ~15, wy0 = k.y - EF_BW_HALF;
-
     // ---- 1. rows -> exclusive row prefixes: P[r+1][a] = sum of the bytes [0, a) of window row r (before the column pass)
     W[lane] = 0;                                                           // P[0][*] = 0
     {
@@ -274,7 +255,7 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
         for (int it = 0; it < EF_BW_ROWS / 8; it++) {
             const int r = 8 * it + g, gy = wy0 + r;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (colok && gy >= 0 && gy < L.h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
+            if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
             // exclusive prefix of the 16 bytes, two 16-bit lanes per register: q[m] = (prefix[2m], prefix[2m+1])
             unsigned q[8];
             unsigned run = 0;
@@ -311,11 +292,56 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
         }
     }
     __syncwarp();
+}
+
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const __grid_constant__ EfPipe p, const EfBadTables t)
+{
+    extern __shared__ __align__(16) unsigned s_win_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.y;
+    const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
+    const int bx = (int)blockIdx.x * p.shard_n + p.shard_i;   // descriptor CTAs dealt round-robin over the GPUs of a band-sharded frame
+    if (bx >= p.total_kpt_blocks) return;
+    int level = p.first_level;
+    while (level + 1 < p.nlevels && bx >= p.lv[level + 1].kpt_block_start) level++;
+    const EfLevel& L = p.lv[level];
+    const int i = (bx - L.kpt_block_start) * EF_DESC_WARPS + warp;
+    if (i >= ctr[level].selected) return;
+    int offset = 0;
+    for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
+    const int row = offset + i;
+    if (row >= p.nfeatures) return;
+
+    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
+    if (p.desc_by_band && (unsigned)((k.y >> 5) - L.own_ty0) >= (unsigned)L.own_rows) return;   // another band's keypoint (warp-uniform)
+    const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
+    const int pitch = L.blur_pitch;
+    unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);
+    const int gx0 = (k.x - EF_BW_HALF) & ~15, wy0 = k.y - EF_BW_HALF;
+    ef_bad_window_integral(W, img, pitch, L.h, gx0, wy0, lane);
 
     const EfBadAffine a = ef_bad_affine((float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, L.w, L.h);
     EfWindowIntegral16 I; I.P = reinterpret_cast<const unsigned short*>(W); I.gx0 = gx0; I.wy0 = wy0;
     uint8_t* out = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch;
     ef_bad_describe(I, a, t, p.desc_bytes * 8, L.w, L.h, out, lane);
+}
+
+// the same window form for a flat keypoint array whose keypoints all have integer coordinates and size 31 at scale 1
+// (the 5 x N GpuMat compute path, cuda_efficient_features.cu:250-263): no full-frame integral image
+__global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_flat_window_kernel(const EfDescJob job, const EfBadTables t)
+{
+    extern __shared__ __align__(16) unsigned s_win_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * EF_DESC_WARPS + warp;
+    if (i >= job.n) return;
+    const float4 k = job.kpts[i];
+    const int kx = (int)k.x, ky = (int)k.y;
+    unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);
+    const int gx0 = (kx - EF_BW_HALF) & ~15, wy0 = ky - EF_BW_HALF;
+    ef_bad_window_integral(W, job.img, job.pitch, job.h, gx0, wy0, lane);
+    const EfBadAffine a = ef_bad_affine(k.x, k.y, k.z, k.w, job.scale, job.w, job.h);
+    EfWindowIntegral16 I; I.P = reinterpret_cast<const unsigned short*>(W); I.gx0 = gx0; I.wy0 = wy0;
+    ef_bad_describe(I, a, t, job.nbits, job.w, job.h, job.desc + (size_t)i * job.desc_pitch, lane);
 }
 
 void ef_launch_bad_pipe(const EfPipe& p, const EfBadTables& t, cudaStream_t s)
@@ -352,5 +378,19 @@ void ef_launch_convert_rows(const float* kpts5, size_t kpts_pitch, int n, float4
 {
     if (n <= 0) return;
     ef_convert_rows_kernel<<<ef_div_up(n, 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(kpts5), kpts_pitch, n, out);
+    EF_COUNT_LAUNCH(1);
+}
+
+void ef_launch_bad_flat_window(const EfDescJob& job, const EfBadTables& t, cudaStream_t s)
+{
+    const size_t smem = (size_t)EF_DESC_WARPS * (EF_BW_ROWS + 1) * EF_BW_WORDS * sizeof(unsigned);
+    static unsigned long long configured = 0;   // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((__atomic_load_n(&configured, __ATOMIC_RELAXED) >> (dev & 63)) & 1ull)) {
+        cudaFuncSetAttribute(ef_bad_flat_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
+    }
+    ef_bad_flat_window_kernel<<<ef_div_up(job.n, EF_DESC_WARPS), EF_DESC_WARPS * 32, smem, s>>>(job, t);
     EF_COUNT_LAUNCH(1);
 }

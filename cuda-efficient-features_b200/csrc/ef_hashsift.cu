@@ -242,6 +242,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     __syncwarp();
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_flat_kernel(const EfDescJob job, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -253,14 +254,16 @@ __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_flat_kernel(co
     const bool valid = i < job.n;
     const int ii = valid ? i : first;
     const float4 k = job.kpts[ii];
-    ef_hashsift_one<false>(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)ii * 128, valid);
+    ef_hashsift_one<STAGED>(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)ii * 128, valid);
 }
 
 void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
 {
     if (job.n <= 0) return;
     const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
-    ef_hashsift_flat_kernel<<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_WARPS * 32, smem, s>>>(job, t, sift128);
+    // staged31: integer keypoints of size 31 at scale 1 (the 5 x N GpuMat compute path) take the window-staging form of the pipeline kernel
+    if (job.staged31) ef_hashsift_flat_kernel<true><<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_WARPS * 32, smem, s>>>(job, t, sift128);
+    else ef_hashsift_flat_kernel<false><<<ef_div_up(job.n, EF_SIFT_KP_PER_CTA), EF_SIFT_WARPS * 32, smem, s>>>(job, t, sift128);
     EF_COUNT_LAUNCH(1);
 }
 

@@ -287,6 +287,8 @@ class ReferenceCuda:
         L.efrefcu_time_detect_levels.argtypes = [C.POINTER(_u8p), C.POINTER(C.c_int), C.POINTER(C.c_int), _f32p, C.POINTER(C.c_int), C.c_int,
                                                  C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int)]
         L.efrefcu_time_detect_levels.restype = C.c_float
+        L.efrefcu_time_hashsift.argtypes = [_u8p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_int, _u8p]
+        L.efrefcu_time_hashsift.restype = C.c_float
 
     @staticmethod
     def available() -> bool:
@@ -326,6 +328,15 @@ class ReferenceCuda:
         sc = np.ascontiguousarray(scales, np.float32); q = (C.c_int * n)(*[int(v) for v in quotas]); out = (C.c_int * n)()
         ms = self.L.efrefcu_time_detect_levels(ptrs, ws, hs, _p(sc, _f32p), q, n, threshold, float(radius), iters, out)
         return float(ms), [int(v) for v in out]
+
+    def time_hashsift(self, img, kpts4, nbits=512, cropping_scale=1.0, iters=20):
+        """the reference's GPU HashSIFT (computePatchSIFTs + cublasSgemm + binarizeDescriptors): (mean ms, descriptors)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        k = np.ascontiguousarray(kpts4, np.float32).reshape(-1, 4)
+        desc = np.zeros((len(k), nbits // 8), np.uint8)
+        ms = self.L.efrefcu_time_hashsift(_p(img, _u8p), w, h, _p(k, _f32p), len(k), nbits, float(cropping_scale), iters, _p(desc, _u8p))
+        return float(ms), desc
 
     def scale(self, xy, scale, octave):
         xy = np.ascontiguousarray(xy, np.int16)

@@ -8,6 +8,9 @@
 
 #include <cuda_fast.cu>                    // -I<reference>/modules/cuda_efficient_features/src
 #include <cuda_efficient_features.cu>
+#include <cuda_hash_sift.cu>             // the reference's GPU HashSIFT kernels (approximately equal to its CPU descriptors: tests/descriptor_test.cpp:48-75)
+
+#include <cublas_v2.h>
 
 using namespace cv;
 using namespace cv::cuda;
@@ -158,6 +161,53 @@ float efrefcu_time_detect_levels(const uint8_t* const* h_levels, const int* ws, 
     cudaStreamDestroy(st);
     cudaFreeHost(h_cnt);
     return (float)(total_ms / iters);
+}
+
+// The reference's GPU HashSIFT (cuda_hash_sift.cpp:113-137): computePatchSIFTs -> cublasSgemm (hashSIFTGemm, :44-60) -> binarizeDescriptors,
+// on n keypoints (x, y, size, angle) of one image.  Returns the mean milliseconds over `iters` (one discarded warm-up) and the descriptors.
+float efrefcu_time_hashsift(const uint8_t* h_img, int w, int h, const float* h_kpts4, int n, int nbits, float croppingScale, int iters, uint8_t* h_desc)
+{
+#include "hash_sift.p512.h"
+#include "hash_sift.p256.h"
+    if (n <= 0 || (nbits != 256 && nbits != 512)) return -1.f;
+    const double* vals = nbits == 512 ? HASH_SIFT_512_VALS : HASH_SIFT_256_VALS;
+    std::vector<float> B((size_t)nbits * 129);
+    for (size_t i = 0; i < B.size(); i++) B[i] = (float)vals[i];                 // Mat(...CV_64F...).convertTo(bMatrix_, CV_32F), :104-106
+    DevBuf img((size_t)w * h), kp(sizeof(float) * 4 * (size_t)n), resp(sizeof(float) * 129 * (size_t)n), tmp(sizeof(float) * (size_t)nbits * n),
+           bm(sizeof(float) * B.size()), desc((size_t)n * (nbits / 8));
+    cudaMemcpy(img.p, h_img, (size_t)w * h, cudaMemcpyHostToDevice);
+    cudaMemcpy(kp.p, h_kpts4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(bm.p, B.data(), sizeof(float) * B.size(), cudaMemcpyHostToDevice);
+    GpuMat gimg(h, w, CV_8UC1, img.p, (size_t)w), gk(n, 1, CV_32FC4, kp.p, sizeof(float) * 4);
+    GpuMat gresp(n, 129, CV_32F, resp.p, sizeof(float) * 129), gtmp(n, nbits, CV_32F, tmp.p, sizeof(float) * (size_t)nbits);
+    GpuMat gB(nbits, 129, CV_32F, bm.p, sizeof(float) * 129), gdesc(n, nbits / 8, CV_8UC1, desc.p, (size_t)(nbits / 8));
+    cublasHandle_t handle;
+    cublasCreate_v2(&handle);
+    cublasSetPointerMode_v2(handle, CUBLAS_POINTER_MODE_HOST);
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    cublasSetStream_v2(handle, st);
+    double total = 0;
+    for (int it = 0; it <= iters; it++) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        gpu::computePatchSIFTs(gimg, gk, gresp, croppingScale, 1.f / 6, 1.6, st);
+        const float alphaf = 1.0f, betaf = 0.0f;
+        cublasSgemm_v2(handle, CUBLAS_OP_T, CUBLAS_OP_N, gB.rows, gresp.rows, gB.cols, &alphaf, gB.ptr<float>(), (int)(gB.step / sizeof(float)),
+                       gresp.ptr<float>(), (int)(gresp.step / sizeof(float)), &betaf, gtmp.ptr<float>(), (int)(gtmp.step / sizeof(float)));
+        gpu::binarizeDescriptors(gtmp, gdesc, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0) total += ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (h_desc) cudaMemcpy(h_desc, desc.p, (size_t)n * (nbits / 8), cudaMemcpyDeviceToHost);
+    cublasDestroy_v2(handle);
+    cudaStreamDestroy(st);
+    return (float)(total / iters);
 }
 
 } // extern "C"

@@ -5,6 +5,7 @@
 #ifndef EF_SHIM_OPENCV_CORE_CUDA_HPP
 #define EF_SHIM_OPENCV_CORE_CUDA_HPP
 
+#include <cfloat>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -16,12 +17,14 @@
 #include <cuda_runtime.h>
 
 #define CV_PI 3.1415926535897932384626433832795
+#define CV_2PI 6.283185307179586476925286766559
 #define CV_CN_SHIFT 3
 #define CV_8U 0
 #define CV_32S 4
 #define CV_32F 5
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
 #define CV_Assert(expr) do { if (!(expr)) { std::fprintf(stderr, "CV_Assert failed: %s (%s:%d)\n", #expr, __FILE__, __LINE__); std::abort(); } } while (0)
 
@@ -60,6 +63,8 @@ template <class T> struct PtrStep {
     T* data; size_t step;
     __host__ __device__ PtrStep() : data(nullptr), step(0) {}
     __host__ __device__ PtrStep(T* d, size_t s) : data(d), step(s) {}
+    __host__ __device__ operator T*() { return data; }                    // DevPtr<T>::operator T*() of OpenCV
+    __host__ __device__ operator const T*() const { return data; }
     __host__ __device__ T* ptr(int y = 0) { return (T*)((char*)data + (size_t)y * step); }
     __host__ __device__ const T* ptr(int y = 0) const { return (const T*)((const char*)data + (size_t)y * step); }
     __host__ __device__ T& operator()(int y, int x) { return ptr(y)[x]; }
@@ -72,6 +77,8 @@ template <class T> struct PtrStepSz : public PtrStep<T> {
 };
 typedef PtrStep<uchar> PtrStepb;
 typedef PtrStepSz<uchar> PtrStepSzb;
+typedef PtrStep<float> PtrStepf;
+typedef PtrStepSz<float> PtrStepSzf;
 
 // device matrix header (no ownership: the shim's users allocate with cudaMalloc and wrap)
 class GpuMat {

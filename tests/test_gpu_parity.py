@@ -420,3 +420,42 @@ def test_compute_only_40k_keypoints_4k(torch_cuda, oracle, dtype_name):
         o = oracle.hashsift(img, k, 1.0, 512)
     assert g.shape == (n, 64)
     assert np.array_equal(g, o), f"{(g != o).any(axis=1).sum()} of {n} descriptors differ"
+
+
+# ---------------------------------------------------------------------------------------------------
+# 5 x N GpuMat compute path (window-staging kernels when the image is 16-byte aligned, generic kernels otherwise):
+# arbitrary integer positions including the border band and outside the detector's 15-px margin, special angles
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype_name", ["BAD_256", "BAD_512", "HASH_SIFT_256", "HASH_SIFT_512"])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_compute_rows_staged_and_generic_paths(torch_cuda, oracle, dtype_name, aligned):
+    import efb200, efo
+    torch = torch_cuda
+    w, h, n = 1000, 700, 6000
+    img = oracle.synth_frame(util.SEED + 24, 0, w, h)
+    rng = np.random.default_rng(11)
+    xs = rng.integers(0, w, n).astype(np.int16); ys = rng.integers(0, h, n).astype(np.int16)
+    xs[:40] = [0, 1, 2, 14, 15, 16, 22, 23, 24, 26, 27, 28, w - 1, w - 2, w - 15, w - 16, w - 23, w - 24, w - 27, w - 28] * 2
+    ys[40:80] = [0, 1, 2, 14, 15, 16, 22, 23, 24, 26, 27, 28, h - 1, h - 2, h - 15, h - 16, h - 23, h - 24, h - 27, h - 28] * 2
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    ang[::7] = np.array([-1.0, 0.0, 90.0, 180.0, 270.0, 359.99, 45.0], np.float32)[np.arange(len(ang[::7])) % 7]
+    rows = np.zeros((5, n), np.float32)
+    rows[0] = np.stack([xs, ys], axis=1).copy().view(np.float32)[:, 0]          # short2 packed into the float row
+    rows[2] = ang
+    rows[4] = 77.0                                                                # ignored: the GpuMat path forces size 31
+    ef = make_ef(nfeatures=100, dtype=getattr(efb200, dtype_name), max_width=w + 8, max_height=h, max_keypoints=n)
+    if aligned:
+        d_img = torch.from_numpy(img).cuda()                                     # pitch 1000 is not a multiple of 16 -> pad to 1008
+        buf = torch.zeros((h, 1008), dtype=torch.uint8, device="cuda")
+        buf[:, :w] = d_img
+        d_img = buf[:, :w]
+        assert d_img.data_ptr() % 16 == 0 and d_img.stride(0) % 16 == 0
+    else:
+        buf = torch.zeros((h, w + 5), dtype=torch.uint8, device="cuda")
+        buf[:, 3:w + 3] = torch.from_numpy(img).cuda()
+        d_img = buf[:, 3:w + 3]                                                   # base and pitch unaligned: generic kernels
+    desc = ef.computeAsync(d_img, torch.from_numpy(rows).cuda())
+    k4 = np.stack([xs.astype(np.float32), ys.astype(np.float32), np.full(n, 31, np.float32), ang], axis=1)
+    o = oracle.bad(img, k4, 1.0, 256 if "256" in dtype_name else 512) if dtype_name.startswith("BAD") else oracle.hashsift(img, k4, 1.0, 256 if "256" in dtype_name else 512)
+    g = desc.cpu().numpy()
+    assert np.array_equal(g, o), f"{(g != o).any(axis=1).sum()} of {n} descriptors differ (first rows {np.nonzero((g != o).any(axis=1))[0][:8]})"

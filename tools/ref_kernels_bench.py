@@ -49,7 +49,43 @@ def main():
         ms, n = ref.time_detect_levels(levels, scales, quotas, 20, 15.0, iters)
         out.append({"frame": name, "reference_kernels_ms": ms, "reference_keypoints": sum(n), "ours_detector_stages_ms": ours_detect,
                     "ours_keypoints": len(kp), "ours_stage_ms": ours, "speedup": ms / ours_detect})
-    print(json.dumps({"detector_kernels_4k_one_frame": out}))
+    # ---- descriptors: the reference's GPU HashSIFT-512 vs ours (compute-only API) on the same 40 000 keypoints of the noise frame
+    img = frames["noise"]
+    det = efb200.EfficientFeatures.create(nf, dtype=efb200.BAD_256, max_width=w, max_height=h)
+    kd = det.detect(torch.from_numpy(img).cuda())
+    k = np.stack([kd["x"], kd["y"], np.full(len(kd), 31.0, np.float32), kd["angle"]], axis=1).astype(np.float32)
+    k = np.concatenate([k, k[: 40000 - len(k)]])[:40000]
+    ms_ref, desc_ref = ref.time_hashsift(img, k, 512, 1.0, 20)
+    hs = efb200.HashSIFT.create(1.0, 100, max_width=w, max_height=h, max_keypoints=40000)
+    dimg = torch.from_numpy(img).cuda(); dk = torch.from_numpy(k).cuda()
+    desc = torch.empty((len(k), 64), dtype=torch.uint8, device="cuda")
+    L, hnd = hs._ef._h.L, hs._ef._h.h
+    # (a) std::vector<KeyPoint> path (arbitrary sizes / sub-pixel positions: generic kernel); (b) 5 x N GpuMat path, the one the reference's
+    # sample_benchmark --benchmark-type=2 times (integer positions, size 31: window-staging kernel)
+    rows = np.zeros((5, len(k)), np.float32)
+    rows[0] = np.stack([k[:, 0].astype(np.int16), k[:, 1].astype(np.int16)], axis=1).copy().view(np.float32)[:, 0]
+    rows[2] = k[:, 3]
+    drows = torch.from_numpy(rows).cuda()
+    def ours_vec():
+        L.ef_compute_async(hnd, dimg.data_ptr(), dimg.stride(0), w, h, dk.data_ptr(), len(k), desc.data_ptr(), 64, efb200._stream_ptr(None))
+    def ours_rows():
+        L.ef_compute_rows_async(hnd, dimg.data_ptr(), dimg.stride(0), w, h, drows.data_ptr(), drows.stride(0) * 4, len(k), desc.data_ptr(), 64, efb200._stream_ptr(None))
+    def timeit(fn):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+    ms_vec = timeit(ours_vec)
+    ms_ours = timeit(ours_rows)
+    cpu = o.hashsift(img, k, 1.0, 512)
+    d = desc.cpu().numpy()
+    bits = lambda a, b: int(np.unpackbits(a ^ b, axis=1).sum())
+    hs_cmp = {"keypoints": len(k), "reference_gpu_ms": ms_ref, "ours_ms": ms_ours, "ours_vector_keypoint_path_ms": ms_vec, "speedup": ms_ref / ms_ours,
+              "bits_differing_from_cpu_reference": {"reference_gpu": bits(desc_ref, cpu), "ours": bits(d, cpu), "of": int(cpu.size * 8)}}
+    print(json.dumps({"detector_kernels_4k_one_frame": out, "hashsift512_compute_40k": hs_cmp}))
 
 
 if __name__ == "__main__":
