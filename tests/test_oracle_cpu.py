@@ -142,3 +142,18 @@ def test_detect_counts_scale(oracle):
     assert 4500 <= len(kp) <= 5000
     assert abs(counts[0, 0] / (1890 * 1050) - 0.25) < 0.02
     assert (kp["octave"][1:] >= kp["octave"][:-1]).all()
+
+
+def test_blur_oracle_within_one_lsb_of_opencv_cpu(oracle):
+    """cv::cuda's Gaussian filter (float row/column passes) cannot run here; OpenCV's CPU GaussianBlur uses 8-bit fixed-point kernels, so it is
+    not bit-comparable -- but taps, kernel size and BORDER_REFLECT_101 handling must put every pixel, borders included, within 1 LSB of it."""
+    cv2 = pytest.importorskip("cv2")
+    for seed, (w, h) in enumerate([(640, 480), (333, 257), (64, 35)]):
+        img = oracle.synth_frame(util.SEED + 70 + seed, 0, w, h)
+        for src in (img, cv2.resize(cv2.resize(img, (max(w // 8, 2), max(h // 8, 2))), (w, h), interpolation=cv2.INTER_CUBIC)):
+            a = oracle.gaussian_blur7(src)
+            b = cv2.GaussianBlur(src, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+            d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+            assert d.max() <= 1
+            border = np.ones_like(d, bool); border[3:-3, 3:-3] = False
+            assert d[border].max() <= 1 and (d[border] > 0).mean() < 0.35
