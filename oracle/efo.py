@@ -289,6 +289,8 @@ class ReferenceCuda:
         L.efrefcu_time_detect_levels.restype = C.c_float
         L.efrefcu_time_hashsift.argtypes = [_u8p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_int, _u8p]
         L.efrefcu_time_hashsift.restype = C.c_float
+        L.efrefcu_time_bad.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_int, _u8p]
+        L.efrefcu_time_bad.restype = C.c_float
 
     @staticmethod
     def available() -> bool:
@@ -336,6 +338,17 @@ class ReferenceCuda:
         k = np.ascontiguousarray(kpts4, np.float32).reshape(-1, 4)
         desc = np.zeros((len(k), nbits // 8), np.uint8)
         ms = self.L.efrefcu_time_hashsift(_p(img, _u8p), w, h, _p(k, _f32p), len(k), nbits, float(cropping_scale), iters, _p(desc, _u8p))
+        return float(ms), desc
+
+    def time_bad(self, img, kpts4, nbits=512, scale_factor=1.0, iters=20):
+        """the reference's GPU BAD kernel (loadBoxPairParams + computeBAD) on an exact int32 integral image built here: (mean ms, descriptors)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        integ = np.zeros((h + 1, w + 1), np.int32)
+        integ[1:, 1:] = np.cumsum(np.cumsum(img.astype(np.int64), axis=0), axis=1).astype(np.int32)
+        k = np.ascontiguousarray(kpts4, np.float32).reshape(-1, 4)
+        desc = np.zeros((len(k), nbits // 8), np.uint8)
+        ms = self.L.efrefcu_time_bad(_p(integ, C.POINTER(C.c_int)), w, h, _p(k, _f32p), len(k), nbits, float(scale_factor), iters, _p(desc, _u8p))
         return float(ms), desc
 
     def scale(self, xy, scale, octave):

@@ -1,5 +1,5 @@
 // ref_cuda_api.cu -- TEST INFRASTRUCTURE: C entry points over the reference's own CUDA detector kernels, compiled UNMODIFIED from
-// /root/reference/modules/cuda_efficient_features/src/{cuda_fast.cu, cuda_efficient_features.cu} against oracle/shim_cuda (default nvcc
+// /root/reference/modules/cuda_efficient_features/src/{cuda_fast, cuda_efficient_features, cuda_hash_sift, cuda_bad}.cu against oracle/shim_cuda (default nvcc
 // flags = the reference's build, modules/cuda_efficient_features/CMakeLists.txt:22-29: contraction on).  Used by tests/ only, to pin the
 // CPU restatement of the detector (oracle/ef_oracle.c) and the product kernels against what the reference really computes:
 // FAST-9 corner set, Harris responses, radius NMS, limitPoints, IC angles, scalePoints.
@@ -9,6 +9,8 @@
 #include <cuda_fast.cu>                    // -I<reference>/modules/cuda_efficient_features/src
 #include <cuda_efficient_features.cu>
 #include <cuda_hash_sift.cu>             // the reference's GPU HashSIFT kernels (approximately equal to its CPU descriptors: tests/descriptor_test.cpp:48-75)
+
+#include <cuda_bad.cu>                   // the reference's GPU BAD kernel (float cos/sin: approximately equal to its CPU descriptors, tests/descriptor_test.cpp:19-46)
 
 #include <cublas_v2.h>
 
@@ -206,6 +208,37 @@ float efrefcu_time_hashsift(const uint8_t* h_img, int w, int h, const float* h_k
     }
     if (h_desc) cudaMemcpy(h_desc, desc.p, (size_t)n * (nbits / 8), cudaMemcpyDeviceToHost);
     cublasDestroy_v2(handle);
+    cudaStreamDestroy(st);
+    return (float)(total / iters);
+}
+
+// The reference's GPU BAD (cuda_bad.cpp:46-70): loadBoxPairParams + computeBAD on n keypoints (x, y, size, angle), given the integral image
+// ((h + 1) x (w + 1) int32, exact prefix sums computed by the caller: cudev's integral is third-party and not part of the timing).
+float efrefcu_time_bad(const int* h_integral, int w, int h, const float* h_kpts4, int n, int nbits, float scaleFactor, int iters, uint8_t* h_desc)
+{
+    if (n <= 0 || (nbits != 256 && nbits != 512)) return -1.f;
+    DevBuf integ(sizeof(int) * (size_t)(w + 1) * (h + 1)), kp(sizeof(float) * 4 * (size_t)n), desc((size_t)n * (nbits / 8));
+    cudaMemcpy(integ.p, h_integral, sizeof(int) * (size_t)(w + 1) * (h + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(kp.p, h_kpts4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice);
+    GpuMat gint(h + 1, w + 1, CV_32S, integ.p, sizeof(int) * (size_t)(w + 1)), gk(n, 1, CV_32FC4, kp.p, sizeof(float) * 4);
+    GpuMat gdesc(n, nbits / 8, CV_8UC1, desc.p, (size_t)(nbits / 8));
+    gpu::loadBoxPairParams(nbits);
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    double total = 0;
+    for (int it = 0; it <= iters; it++) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        gpu::computeBAD(gint, gk, gdesc, scaleFactor, nbits, Size(32, 32), st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0) total += ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (h_desc) cudaMemcpy(h_desc, desc.p, (size_t)n * (nbits / 8), cudaMemcpyDeviceToHost);
     cudaStreamDestroy(st);
     return (float)(total / iters);
 }

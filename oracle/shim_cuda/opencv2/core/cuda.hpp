@@ -26,6 +26,7 @@
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
+#define CV_Error(code, msg) do { std::fprintf(stderr, "CV_Error: %s (%s:%d)\n", msg, __FILE__, __LINE__); std::abort(); } while (0)
 #define CV_Assert(expr) do { if (!(expr)) { std::fprintf(stderr, "CV_Assert failed: %s (%s:%d)\n", #expr, __FILE__, __LINE__); std::abort(); } } while (0)
 
 namespace cv
@@ -39,6 +40,8 @@ static inline int cvRound(double v) { return (int)std::lrint(v); }
 
 struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} int area() const { return width * height; } };
 struct Point2f { float x = 0, y = 0; };
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {} };
+namespace Error { enum Code { StsBadArg = -5 }; }
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
 
 class _InputArray { };
@@ -56,6 +59,7 @@ struct Mat {
 namespace cuda
 {
 class Stream { public: static Stream& Null() { static Stream s; return s; } };
+struct StreamAccessor { static cudaStream_t getStream(const Stream&) { return 0; } };
 
 static inline __host__ __device__ int divUp(int total, int grain) { return (total + grain - 1) / grain; }
 
@@ -79,6 +83,8 @@ typedef PtrStep<uchar> PtrStepb;
 typedef PtrStepSz<uchar> PtrStepSzb;
 typedef PtrStep<float> PtrStepf;
 typedef PtrStepSz<float> PtrStepSzf;
+typedef PtrStep<int> PtrStepi;
+typedef PtrStepSz<int> PtrStepSzi;
 
 // device matrix header (no ownership: the shim's users allocate with cudaMalloc and wrap)
 class GpuMat {
@@ -91,6 +97,10 @@ public:
     int type() const { return flags; }
     Size size() const { return Size(cols, rows); }
     void release() { rows = cols = 0; }   // header only: the memory belongs to the caller
+    // allocation / fill / ROI are only reached through calcIntegralImage, which the test wrappers never call
+    void create(int, int, int) { std::fprintf(stderr, "GpuMat::create is not available in the shim\n"); std::abort(); }
+    template <class S> void setTo(int, S&) { std::abort(); }
+    GpuMat operator()(const Rect& r) const { GpuMat m = *this; m.data = data + (size_t)r.y * step + (size_t)r.x * 4; m.rows = r.height; m.cols = r.width; return m; }
     template <class T> T* ptr(int y = 0) { return reinterpret_cast<T*>(data + (size_t)y * step); }
     template <class T> const T* ptr(int y = 0) const { return reinterpret_cast<const T*>(data + (size_t)y * step); }
     template <class T> operator PtrStepSz<T>() const { return PtrStepSz<T>(rows, cols, (T*)data, step); }

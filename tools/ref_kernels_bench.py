@@ -85,7 +85,22 @@ def main():
     bits = lambda a, b: int(np.unpackbits(a ^ b, axis=1).sum())
     hs_cmp = {"keypoints": len(k), "reference_gpu_ms": ms_ref, "ours_ms": ms_ours, "ours_vector_keypoint_path_ms": ms_vec, "speedup": ms_ref / ms_ours,
               "bits_differing_from_cpu_reference": {"reference_gpu": bits(desc_ref, cpu), "ours": bits(d, cpu), "of": int(cpu.size * 8)}}
-    print(json.dumps({"detector_kernels_4k_one_frame": out, "hashsift512_compute_40k": hs_cmp}))
+    # ---- BAD-512: the reference's GPU kernel (integral image excluded on its side: cudev is third-party) vs ours (5 x N path, window integral included)
+    ms_bref, bdesc_ref = ref.time_bad(img, k, 512, 1.0, 20)
+    bad = efb200.BAD.create(1.0, 100, max_width=w, max_height=h, max_keypoints=40000)
+    Lb, hb = bad._ef._h.L, bad._ef._h.h
+    def ours_bad_rows():
+        Lb.ef_compute_rows_async(hb, dimg.data_ptr(), dimg.stride(0), w, h, drows.data_ptr(), drows.stride(0) * 4, len(k), desc.data_ptr(), 64, efb200._stream_ptr(None))
+    def ours_bad_vec():
+        Lb.ef_compute_async(hb, dimg.data_ptr(), dimg.stride(0), w, h, dk.data_ptr(), len(k), desc.data_ptr(), 64, efb200._stream_ptr(None))
+    ms_bvec = timeit(ours_bad_vec)
+    ms_bours = timeit(ours_bad_rows)
+    bcpu = o.bad(img, k, 1.0, 512)
+    bd = desc.cpu().numpy()
+    bad_cmp = {"keypoints": len(k), "reference_gpu_kernel_ms_without_integral": ms_bref, "ours_ms": ms_bours, "ours_vector_keypoint_path_ms_with_integral": ms_bvec,
+               "speedup": ms_bref / ms_bours,
+               "bits_differing_from_cpu_reference": {"reference_gpu": bits(bdesc_ref, bcpu), "ours": bits(bd, bcpu), "of": int(bcpu.size * 8)}}
+    print(json.dumps({"detector_kernels_4k_one_frame": out, "hashsift512_compute_40k": hs_cmp, "bad512_compute_40k": bad_cmp}))
 
 
 if __name__ == "__main__":
