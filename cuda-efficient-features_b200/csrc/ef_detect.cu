@@ -767,7 +767,8 @@ __device__ __forceinline__ int ef_block_excl_scan_flag(bool f, int* s_warp /*[33
     return r;
 }
 
-__global__ void __launch_bounds__(1024) ef_select_kernel(const __grid_constant__ EfPipe p)
+#define EF_SEL_E 16          // survivors per thread the register-resident select holds (16 K per level: every level of a 4K frame)
+__global__ void __launch_bounds__(1024, 1) ef_select_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ int s_warp[33];
     __shared__ unsigned s_hist[256];
@@ -815,26 +816,130 @@ __global__ void __launch_bounds__(1024) ef_select_kernel(const __grid_constant__
         return;
     }
 
+    if (quota <= 0) {
+        // a level whose share of nfeatures rounds to zero (nfeatures = 1): nothing is selected, and the digit search below needs k >= 1
+        if (tid == 0) { ctr->survivors = ntotal; ctr->selected = 0; ctr->overflow = ncand > L.surv_cap; }
+        return;
+    }
+    if (n <= EF_SEL_E * 1024) {
+        // ---- register-resident form (every level of a 4K frame): thread t owns the contiguous run [t E, (t + 1) E) of the raster-ordered
+        //      list, loaded ONCE; the four radix passes and the final ordered compaction then touch no global memory, and the two block-wide
+        //      prefix sums (selected / tied elements before this thread's run) replace two scans per 1024 elements.
+        const int E = (n + 1023) >> 10, base = tid * E;
+        unsigned key[EF_SEL_E];
+#pragma unroll
+        for (int e = 0; e < EF_SEL_E; e++) {
+            const int i = base + e;
+            const bool in = e < E && i < n;
+            key[e] = in ? ef_float_key(surv[i].resp) : 0u;       // key 0 never occurs for a real response (finite floats map above 0)
+        }
+        unsigned prefix = 0, pmask = 0;
+        int k = quota;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < EF_SEL_E; e++) {
+                const bool in = key[e] != 0u && (key[e] & pmask) == prefix;
+                const unsigned part = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const unsigned digit = (key[e] >> shift) & 255u;
+                    const unsigned peers = __match_any_sync(part, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (tid < 256) {
+                const unsigned hcnt = s_hist[tid];
+                unsigned suf = hcnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned u = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + o < 32) suf += u;
+                }
+                if (lane == 0) s_warp[warp] = (int)suf;
+                __syncwarp();
+                asm volatile("bar.sync 1, 256;");
+                unsigned above = 0;
+                for (int wv = warp + 1; wv < 8; wv++) above += (unsigned)s_warp[wv];
+                const unsigned incl = suf + above, excl = incl - hcnt;
+                if ((int)excl < k && k <= (int)incl) { s_prefix = prefix | ((unsigned)tid << shift); s_k = k - (int)excl; }
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            k = s_k;
+            pmask |= 0xffu << shift;
+            __syncthreads();
+        }
+        const unsigned T = prefix;   // key of the quota-th largest; k = how many keys == T are still needed (the first k in raster order)
+        int my_eq = 0, my_gt = 0;
+#pragma unroll
+        for (int e = 0; e < EF_SEL_E; e++) { my_eq += key[e] == T; my_gt += key[e] > T; }
+        // exclusive block prefix of (tied, larger) counts: warp scan + warp totals
+        int inc_eq = my_eq, inc_gt = my_gt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, inc_eq, o), b = __shfl_up_sync(0xffffffffu, inc_gt, o);
+            if (lane >= o) { inc_eq += a; inc_gt += b; }
+        }
+        __shared__ int s_weq[32], s_wgt[32];
+        if (lane == 31) { s_weq[warp] = inc_eq; s_wgt[warp] = inc_gt; }
+        __syncthreads();
+        int eq_before = inc_eq - my_eq, gt_before = inc_gt - my_gt;
+        for (int wv = 0; wv < warp; wv++) { eq_before += s_weq[wv]; gt_before += s_wgt[wv]; }
+        // output position of an element = (larger keys before it) + (tied keys before it that are taken)
+        int pos = gt_before + min(eq_before, k), eqr = eq_before;
+#pragma unroll
+        for (int e = 0; e < EF_SEL_E; e++) {
+            const bool eq = key[e] == T, take = key[e] > T || (eq && eqr < k);
+            if (take && pos < quota) {
+                const EfSurvivor sv = surv[base + e];
+                EfSelected o; o.x = sv.x; o.y = sv.y; o.resp = sv.resp; o.angle = 0.f; o.pad = 0;
+                sel[pos] = o;
+            }
+            pos += take; eqr += eq;
+        }
+        if (tid == 1023) { ctr->survivors = ntotal; ctr->selected = min(pos, quota); ctr->overflow = ncand > L.surv_cap; }
+        return;
+    }
+
     // radix select: key of the quota-th largest response
     unsigned prefix = 0, pmask = 0;
     int k = quota;
     for (int shift = 24; shift >= 0; shift -= 8) {
         if (tid < 256) s_hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += 1024) {
-            const unsigned key = ef_float_key(surv[i].resp);
-            if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        // responses of one level share their leading key bytes: aggregate the histogram updates per warp (one atomic per distinct
+        // digit and warp) instead of thousands of same-address shared-memory atomics
+        for (int start = 0; start < n; start += 1024) {
+            const int i = start + tid;
+            unsigned key = 0;
+            bool in = false;
+            if (i < n) { key = ef_float_key(surv[i].resp); in = (key & pmask) == prefix; }
+            const unsigned part = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned digit = (key >> shift) & 255u;
+                const unsigned peers = __match_any_sync(part, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+            }
         }
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0, b = 255;
-            for (; b > 0; b--) {
-                const int hcnt = (int)s_hist[b];
-                if (acc + hcnt >= k) break;
-                acc += hcnt;
+        // the digit b with  sum(hist[b+1..255]) < k <= sum(hist[b..255]):  suffix sums by 256 threads (8 warps) instead of one thread's loop
+        if (tid < 256) {
+            const unsigned hcnt = s_hist[tid];
+            unsigned suf = hcnt;                                   // inclusive suffix sum inside the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += u;
             }
-            s_prefix = prefix | ((unsigned)b << shift);
-            s_k = k - acc;
+            if (lane == 0) s_warp[warp] = (int)suf;                // warp totals (warps 0..7)
+            __syncwarp();
+            asm volatile("bar.sync 1, 256;");                     // the 8 participating warps only
+            unsigned above = 0;                                    // counts of the warps holding larger digits
+            for (int wv = warp + 1; wv < 8; wv++) above += (unsigned)s_warp[wv];
+            const unsigned incl = suf + above, excl = incl - hcnt; // sum(hist[tid..255]), sum(hist[tid+1..255])
+            if ((int)excl < k && k <= (int)incl) { s_prefix = prefix | ((unsigned)tid << shift); s_k = k - (int)excl; }
         }
         __syncthreads();
         prefix = s_prefix;
