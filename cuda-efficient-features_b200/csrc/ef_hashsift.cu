@@ -108,36 +108,46 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         }
         const float cx0 = M00 * (float)hl, cx1 = M00 * (float)(hl + 16);
         const float cy0 = M10 * (float)hl, cy1 = M10 * (float)(hl + 16);
-#pragma unroll 4
-        for (int y = 0; y < 32; y++) {
-            const float ru = M01 * (float)y, rv = M11 * (float)y;
-#pragma unroll
-            for (int xx = 0; xx < 2; xx++) {
-                const float u = ((xx ? cx1 : cx0) + ru) + M02;
-                const float v = ((xx ? cy1 : cy0) + rv) + M12;
-                uint8_t dstVal = 0;
-                const int ui = (int)floorf(u);
-                const int vi = (int)floorf(v);
-                if (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h) {
-                    const float du = u - (float)ui;
-                    const float dv = v - (float)vi;
-                    float q00, q01, q10, q11;
-                    if (STAGED) {
-                        const unsigned short* __restrict__ q = reinterpret_cast<const unsigned short*>(base + (vi - oy) * EF_SIFT_WIN_PITCH) + (ui - ox);
-                        const unsigned t0 = q[0], t1 = q[EF_SIFT_WIN_PITCH / 2];
-                        q00 = (float)(t0 & 0xffu); q01 = (float)(t0 >> 8); q10 = (float)(t1 & 0xffu); q11 = (float)(t1 >> 8);
-                    } else {
-                        const uint8_t* __restrict__ q = base + (vi - oy) * bpitch + (ui - ox);
-                        q00 = (float)q[0]; q01 = (float)q[1]; q10 = (float)q[bpitch]; q11 = (float)q[bpitch + 1];
-                    }
-                    const float tmp0 = (1 - du) * q00 + du * q01;
-                    const float tmp1 = (1 - du) * q10 + du * q11;
-                    const float tmp2 = (1 - dv) * tmp0 + dv * tmp1;
-                    dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255);
-                }
-                patch[y * 32 + hl + 16 * xx] = dstVal;
-            }
+        // STAGED: when the whole 48 x 48 window of both keypoints of the warp lies inside the image, every sample does (all of them fall
+        // in [k - 22, k + 22]) and the four bounds tests per sample are dropped (warp-uniform choice; same arithmetic)
+        bool inside = false;
+        if (STAGED) {
+            const int ikx = (int)kx, iky = (int)ky;
+            inside = __all_sync(0xffffffffu, ikx >= EF_SIFT_WIN / 2 && ikx + EF_SIFT_WIN / 2 < w && iky >= EF_SIFT_WIN / 2 && iky + EF_SIFT_WIN / 2 < h);
         }
+#define EF_SIFT_SAMPLE_ROWS(CHECK) \
+        _Pragma("unroll 4") \
+        for (int y = 0; y < 32; y++) { \
+            const float ru = M01 * (float)y, rv = M11 * (float)y; \
+            _Pragma("unroll") \
+            for (int xx = 0; xx < 2; xx++) { \
+                const float u = ((xx ? cx1 : cx0) + ru) + M02; \
+                const float v = ((xx ? cy1 : cy0) + rv) + M12; \
+                uint8_t dstVal = 0; \
+                const int ui = (int)floorf(u); \
+                const int vi = (int)floorf(v); \
+                if (!(CHECK) || (ui >= 0 && ui + 1 < w && vi >= 0 && vi + 1 < h)) { \
+                    const float du = u - (float)ui; \
+                    const float dv = v - (float)vi; \
+                    float q00, q01, q10, q11; \
+                    if (STAGED) { \
+                        const unsigned short* __restrict__ q = reinterpret_cast<const unsigned short*>(base + (vi - oy) * EF_SIFT_WIN_PITCH) + (ui - ox); \
+                        const unsigned t0 = q[0], t1 = q[EF_SIFT_WIN_PITCH / 2]; \
+                        q00 = (float)(t0 & 0xffu); q01 = (float)(t0 >> 8); q10 = (float)(t1 & 0xffu); q11 = (float)(t1 >> 8); \
+                    } else { \
+                        const uint8_t* __restrict__ q = base + (vi - oy) * bpitch + (ui - ox); \
+                        q00 = (float)q[0]; q01 = (float)q[1]; q10 = (float)q[bpitch]; q11 = (float)q[bpitch + 1]; \
+                    } \
+                    const float tmp0 = (1 - du) * q00 + du * q01; \
+                    const float tmp1 = (1 - du) * q10 + du * q11; \
+                    const float tmp2 = (1 - dv) * tmp0 + dv * tmp1; \
+                    dstVal = (uint8_t)min(__float2int_rz(tmp2 + 0.5f), 255); \
+                } \
+                patch[y * 32 + hl + 16 * xx] = dstVal; \
+            } \
+        }
+        if (inside) { EF_SIFT_SAMPLE_ROWS(false) } else { EF_SIFT_SAMPLE_ROWS(true) }
+#undef EF_SIFT_SAMPLE_ROWS
     }
     __syncwarp();
     // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu).
