@@ -16,6 +16,8 @@
 #include "ef_common.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
+#include <cstring>
 
 // =================================================================================================
 // pyramid: bilinear x(1/scaleFactor) chain, one launch per level over the whole batch
@@ -179,10 +181,194 @@ __global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_const
     }
 }
 
+// 16-byte form of the tiled kernel (source image base, frame stride and pitch 16-byte aligned; ratios <= 1.21 x 1.22): one CTA =
+// 128 x 64 output pixels, i.e. 32 pixels per thread, so that the per-thread column geometry and the CTA-wide staging are paid
+// once per 32 pixels instead of once per 16.
+//  * staging: the source window (<= 176 x 78 pixels, first column rounded down to a multiple of 16) is read with one 16-byte load
+//    per 16 pixels, all loads of a thread issued back to back, and converted with packed adds (add.rn.f32x2).  A warp stages a
+//    block of 8 rows x 4 chunks (lane = row + 8 * chunk): 64 contiguous bytes per row on the global side, and on the shared side
+//    the eight lanes of a quarter-warp write eight rows whose 720-byte pitch puts their 16-byte stores on distinct bank groups.
+//  * row geometry (staged row offset, wy1, wy2, "top row must be reloaded") of the 64 output rows is computed once per CTA into
+//    a table read back as one broadcast 16-byte load per row.
+//  * a warp owns 8 CONSECUTIVE output rows: the bottom source row of output row y is the top source row of y + 1 whenever the
+//    source row advances by one (5 rows out of 6 at ratio 1.2), so its taps stay in registers (two register sets swapping roles
+//    in a 2x unrolled loop; the reload is a warp-uniform branch): 2.4 instead of 4 shared-memory loads per pixel -- the loads,
+//    two-way bank-conflicted by the 4.8-word lane stride, are what bounds this kernel.
+// Tap arithmetic = ef_resize_kernel bit for bit (same products, same FMA chain, per-lane IEEE packed fp32).
+#define RS3_TW 128
+#define RS3_TH 64
+#define RS3_RWP 180
+#define RS3_RH 78
+#define RS3_CH 11     // 16-pixel chunks per staged row
+#define RS3_RG ((RS3_RH + 7) / 8)
+struct __align__(16) EfRowGeo { int off; float wy1, wy2; int reload; };
+#define RS3_SMEM (RS3_RH * RS3_RWP * 4 + RS3_TH * 16)
+static_assert(RS3_RG * 3 <= 4 * 8, "staging: at most four 8-row x 4-chunk blocks per warp");
+
+__device__ __forceinline__ float4 ef_u8x4_to_f32x4(unsigned word)
+{
+    // 0x4B0000bb = 2^23 + b: subtracting 2^23 is exact; two bytes per packed add
+    const unsigned long long m = ef_pack2(-8388608.f, -8388608.f);
+    unsigned long long lo = ef_pack2(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)));
+    unsigned long long hi = ef_pack2(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)), __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7543)));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(lo) : "l"(m));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(hi) : "l"(m));
+    float4 f;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(lo));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f.z), "=f"(f.w) : "l"(hi));
+    return f;
+}
+
+struct EfTaps { unsigned long long a0, b0, a1, b1; };   // (px0, px1) / (px2, px3) left taps, then right taps, of one source row
+
+__global__ void __launch_bounds__(256, 4) ef_resize_tiled16_kernel(const __grid_constant__ EfPipe p, const int level)
+{
+    extern __shared__ __align__(16) float s_dyn[];
+    float* __restrict__ s_src = s_dyn;
+    EfRowGeo* __restrict__ s_row = reinterpret_cast<EfRowGeo*>(s_dyn + RS3_RH * RS3_RWP);
+
+    const EfLevel& L = p.lv[level];
+    const EfLevel& S = p.lv[level - 1];
+    const int frame = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * RS3_TW, Y0 = blockIdx.y * RS3_TH;
+
+    int spitch;
+    const uint8_t* __restrict__ src = ef_level_image(p, frame, level - 1, spitch);
+
+    const int xlast = min(X0 + RS3_TW, L.w) - 1, ylast = min(Y0 + RS3_TH, L.h) - 1;
+    const int sx0 = __float2int_rd((float)X0 * L.rx) & ~15;
+    const int sy0 = __float2int_rd((float)Y0 * L.ry);
+    const int nch = min((__float2int_rd((float)xlast * L.rx) + 1 - sx0) / 16 + 1, RS3_CH);
+    const int nrows = min(__float2int_rd((float)ylast * L.ry) + 1 - sy0 + 1, RS3_RH);
+
+    // row geometry of the tile's output rows (rows past the level's last one repeat it; they are never written)
+    if (tid < RS3_TH) {
+        const int y = min(Y0 + tid, L.h - 1);
+        const float sy = (float)y * L.ry;
+        const int y1 = __float2int_rd(sy);
+        const int yp = min(Y0 + tid - 1, L.h - 1);
+        const int offp = min(__float2int_rd((float)yp * L.ry) - sy0, RS3_RH - 2) * (RS3_RWP * 4);
+        EfRowGeo g;
+        g.off = min(y1 - sy0, RS3_RH - 2) * (RS3_RWP * 4); // bytes
+        g.wy1 = (float)(y1 + 1) - sy; g.wy2 = sy - (float)y1;
+        g.reload = ((tid & 7) == 0 || g.off != offp + RS3_RWP * 4) ? 1 : 0;  // first row of a warp, or the source row advanced by two
+        s_row[tid] = g;
+    }
+    // source window: staged row r = source row min(sy0 + r, S.h - 1), staged column c = source column min(sx0 + c, S.w - 1).
+    // Chunks that reach past the last source column (right image edge only) are staged byte-wise with the clamp afterwards.
+    {
+        uint4 v[4];
+        int dsto[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = warp + 8 * k;                      // block of 8 rows x 4 chunks
+            const int rg = b / 3, cg = b - 3 * rg;
+            const int row = 8 * rg + (lane & 7), c = 4 * cg + (lane >> 3);
+            const int gx = sx0 + 16 * c;
+            const bool fast = row < nrows && c < nch && gx + 15 < S.w;
+            dsto[k] = fast ? row * RS3_RWP + 16 * c : -1;
+            if (fast) v[k] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)min(sy0 + row, S.h - 1) * spitch + gx));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (dsto[k] >= 0) {
+                float4* d = reinterpret_cast<float4*>(s_src + dsto[k]);
+                d[0] = ef_u8x4_to_f32x4(v[k].x); d[1] = ef_u8x4_to_f32x4(v[k].y); d[2] = ef_u8x4_to_f32x4(v[k].z); d[3] = ef_u8x4_to_f32x4(v[k].w);
+            }
+        }
+        const int cedge = (S.w - sx0) >> 4;     // first chunk with gx + 15 >= S.w
+        if (cedge < nch) {
+            const int nedge = nch - cedge;
+            for (int i = tid; i < nrows * nedge * 4; i += 256) {
+                const int row = i / (nedge * 4), wq = i - row * (nedge * 4);
+                const uint8_t* rp = src + (size_t)min(sy0 + row, S.h - 1) * spitch;
+                const int g0 = sx0 + 16 * cedge + 4 * wq;
+                const unsigned wd = (unsigned)rp[min(g0, S.w - 1)] | ((unsigned)rp[min(g0 + 1, S.w - 1)] << 8) |
+                                    ((unsigned)rp[min(g0 + 2, S.w - 1)] << 16) | ((unsigned)rp[min(g0 + 3, S.w - 1)] << 24);
+                *reinterpret_cast<float4*>(s_src + row * RS3_RWP + 16 * cedge + 4 * wq) = ef_u8x4_to_f32x4(wd);
+            }
+        }
+    }
+    __syncthreads();
+
+    const int x0 = X0 + 4 * lane;
+    if (x0 >= L.w) return;
+    int o[4];
+    float wx1[4], wx2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = min(x0 + j, L.w - 1);
+        const float sx = (float)x * L.rx;
+        const int x1 = __float2int_rd(sx);
+        o[j] = min(x1 - sx0, RS3_RWP - 2);
+        wx1[j] = (float)(x1 + 1) - sx; wx2[j] = sx - (float)x1;
+    }
+    const unsigned long long wx1a = ef_pack2(wx1[0], wx1[1]), wx1b = ef_pack2(wx1[2], wx1[3]);
+    const unsigned long long wx2a = ef_pack2(wx2[0], wx2[1]), wx2b = ef_pack2(wx2[2], wx2[3]);
+    const int r0 = (RS3_TH / 8) * warp;
+    const int nr = min(RS3_TH / 8, L.h - (Y0 + r0));       // rows of this warp inside the level
+    uint8_t* dst = ef_ws(p, frame, L.img_off) + (size_t)(Y0 + r0) * L.img_pitch + x0;
+    const size_t dpitch = (size_t)L.img_pitch;
+    // tap pointers of row offset 0; the per-row byte offset is added to each (one integer add per pointer and row)
+    const char* qb0 = reinterpret_cast<const char*>(s_src + o[0]); const char* qb1 = reinterpret_cast<const char*>(s_src + o[1]);
+    const char* qb2 = reinterpret_cast<const char*>(s_src + o[2]); const char* qb3 = reinterpret_cast<const char*>(s_src + o[3]);
+
+    auto load_taps = [&](EfTaps& t, int offb) {
+        const float* q0 = reinterpret_cast<const float*>(qb0 + offb); const float* q1 = reinterpret_cast<const float*>(qb1 + offb);
+        const float* q2 = reinterpret_cast<const float*>(qb2 + offb); const float* q3 = reinterpret_cast<const float*>(qb3 + offb);
+        t.a0 = ef_pack2(q0[0], q1[0]); t.b0 = ef_pack2(q2[0], q3[0]);
+        t.a1 = ef_pack2(q0[1], q1[1]); t.b1 = ef_pack2(q2[1], q3[1]);
+    };
+    auto emit_row = [&](const EfTaps& top, const EfTaps& bot, const EfRowGeo& g) {
+        const unsigned long long wy1p = ef_pack2(g.wy1, g.wy1), wy2p = ef_pack2(g.wy2, g.wy2);
+        // tap order = ef_resize_kernel: (y1,x1) (y1,x2) (y2,x1) (y2,x2)
+        unsigned long long a = ef_mul2(top.a0, ef_mul2(wx1a, wy1p));
+        unsigned long long b = ef_mul2(top.b0, ef_mul2(wx1b, wy1p));
+        a = ef_fma2(top.a1, ef_mul2(wx2a, wy1p), a);
+        b = ef_fma2(top.b1, ef_mul2(wx2b, wy1p), b);
+        a = ef_fma2(bot.a0, ef_mul2(wx1a, wy2p), a);
+        b = ef_fma2(bot.b0, ef_mul2(wx1b, wy2p), b);
+        a = ef_fma2(bot.a1, ef_mul2(wx2a, wy2p), a);
+        b = ef_fma2(bot.b1, ef_mul2(wx2b, wy2p), b);
+        float o0, o1, o2, o3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(a));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o2), "=f"(o3) : "l"(b));
+        const unsigned packed = __byte_perm(__byte_perm(ef_sat_u8_rne(o0), ef_sat_u8_rne(o1), 0x0040), __byte_perm(ef_sat_u8_rne(o2), ef_sat_u8_rne(o3), 0x0040), 0x5410);
+        *reinterpret_cast<unsigned*>(dst) = packed; // img_pitch is a multiple of 128
+        dst += dpitch;
+    };
+    EfTaps X, Y;
+#pragma unroll
+    for (int r = 0; r < RS3_TH / 8; r += 2) {
+        if (r >= nr) break;
+        {
+            const EfRowGeo g = s_row[r0 + r];
+            if (g.reload) load_taps(X, g.off);              // warp-uniform
+            load_taps(Y, g.off + RS3_RWP * 4);
+            emit_row(X, Y, g);
+        }
+        if (r + 1 >= nr) break;
+        {
+            const EfRowGeo g = s_row[r0 + r + 1];
+            if (g.reload) load_taps(Y, g.off);
+            load_taps(X, g.off + RS3_RWP * 4);
+            emit_row(Y, X, g);
+        }
+    }
+}
+
+static const bool g_ef_resize_legacy = getenv("EF_RESIZE") && !strcmp(getenv("EF_RESIZE"), "legacy");
 void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
 {
     for (int l = 1; l < p.nlevels; l++) {
-        if (p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.25f) {
+        const bool src16 = l > 1 || ((reinterpret_cast<uintptr_t>(p.img0) | p.img0_stride | (unsigned long long)p.img0_pitch) & 15ull) == 0;
+        if (src16 && p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.22f && !g_ef_resize_legacy) {
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(ef_resize_tiled16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS3_SMEM); attr_set = true; }
+            const dim3 grid(ef_div_up(p.lv[l].w, RS3_TW), ef_div_up(p.lv[l].h, RS3_TH), p.nframes);
+            ef_resize_tiled16_kernel<<<grid, 256, RS3_SMEM, s>>>(p, l);
+        } else if (p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.25f) {
             const dim3 grid(ef_div_up(p.lv[l].w, RS_TW), ef_div_up(p.lv[l].h, RS_TH), p.nframes);
             ef_resize_tiled_kernel<<<grid, 256, 0, s>>>(p, l);
         } else {

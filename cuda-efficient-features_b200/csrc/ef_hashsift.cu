@@ -36,12 +36,16 @@
 
 struct EfSiftWarpSmem {                 // per warp = 2 keypoints
     float hist[9 * 32];                 // [bin 0..8][lane]
+    // the two patches lie 16736 bytes apart = 24 banks (mod 32): the 16-byte runs the two half-warps touch in the same instruction
+    // (sample stores, gradient neighbour loads) fall on different banks
+    uint8_t patch0[32 * 32];
     // per keypoint k: magnitude[i] (sign bit = bin bit 2) at rec[k][k + i], fraction[i] (bits 31:30 = bin bits 1:0) at
     // rec[k][REC + k + i]: the "+ k" puts the second keypoint on the other bank parity.  Phase 1 aliases the staging window here.
     __align__(16) float rec[2][EF_SIFT_BLK + 4];
     float desc[2][128];
-    uint8_t patch[2][32 * 32];
+    uint8_t patch1[32 * 32];
 };
+static_assert(sizeof(EfSiftWarpSmem) == 18912, "6 CTAs of 2 warps per SM need <= 18912 bytes per warp");
 static_assert(EF_SIFT_WIN * EF_SIFT_WIN_PITCH <= EF_SIFT_BLK * 4, "staging window must fit the record block it aliases");
 static_assert((EF_SIFT_BLK + 4) % 4 == 0, "record blocks must stay 16-byte aligned");
 
@@ -70,7 +74,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                                                 const EfHashSiftTables& t, EfSiftWarpSmem& sm, uint8_t* out128, bool store)
 {
     const int lane = threadIdx.x & 31, hl = lane & 15, k = lane >> 4;
-    uint8_t* __restrict__ patch = sm.patch[k];
+    uint8_t* __restrict__ patch = k ? sm.patch1 : sm.patch0;
     // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
     {
         const float PI_1_0F = 3.14159274f;
