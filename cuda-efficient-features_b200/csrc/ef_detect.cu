@@ -95,6 +95,13 @@ __device__ __forceinline__ unsigned long long ef_fma2(unsigned long long a, unsi
     return r;
 }
 
+__device__ __forceinline__ unsigned long long ef_add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_constant__ EfPipe p, const int level)
 {
     __shared__ __align__(16) float s_src[RS_RH * RS_RWP];
@@ -1314,18 +1321,26 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4); i += 256) {
         const int ly = i >> 4, c = i & 15;
         const unsigned w0 = s_in[ly][c], w1 = s_in[ly][c + 1], w2 = s_in[ly][c + 2];
-        float f[10];
-        f[0] = ef_byte_to_float(w0, 1); f[1] = ef_byte_to_float(w0, 2); f[2] = ef_byte_to_float(w0, 3);
-        f[3] = ef_byte_to_float(w1, 0); f[4] = ef_byte_to_float(w1, 1); f[5] = ef_byte_to_float(w1, 2); f[6] = ef_byte_to_float(w1, 3);
-        f[7] = ef_byte_to_float(w2, 0); f[8] = ef_byte_to_float(w2, 1); f[9] = ef_byte_to_float(w2, 2);
-        float o[4];
+        // packed fp32 (fma.rn.f32x2, per-lane IEEE = the scalar chain): outputs (0,1) and (2,3) advance together; tap k multiplies the
+        // input pair (k, k+1) resp. (k+2, k+3).  Pairs starting at an even / odd input are converted separately (E[m] = inputs 2m,
+        // 2m+1; O[m] = inputs 2m+1, 2m+2) so that every pair is born in an aligned register pair.
+        const unsigned long long m23 = ef_pack2(-8388608.f, -8388608.f);
+#define BL_PAIR(wa, ia, wb, ib) ef_add2(ef_pack2(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7540 + (ia))), \
+                                                 __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540 + (ib)))), m23)
+        unsigned long long E[5], O[4];
+        E[0] = BL_PAIR(w0, 1, w0, 2); E[1] = BL_PAIR(w0, 3, w1, 0); E[2] = BL_PAIR(w1, 1, w1, 2); E[3] = BL_PAIR(w1, 3, w2, 0); E[4] = BL_PAIR(w2, 1, w2, 2);
+        O[0] = BL_PAIR(w0, 2, w0, 3); O[1] = BL_PAIR(w1, 0, w1, 1); O[2] = BL_PAIR(w1, 2, w1, 3); O[3] = BL_PAIR(w2, 0, w2, 1);
+#undef BL_PAIR
+        unsigned long long s01 = 0ull, s23 = 0ull;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < 7; k++) sum = fmaf(f[j + k], taps[k], sum);
-            o[j] = sum;
+        for (int k = 0; k < 7; k++) {
+            const unsigned long long tk = ef_pack2(taps[k], taps[k]);
+            s01 = ef_fma2((k & 1) ? O[k >> 1] : E[k >> 1], tk, s01);
+            s23 = ef_fma2((k & 1) ? O[(k >> 1) + 1] : E[(k >> 1) + 1], tk, s23);
         }
+        float o[4];
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o[0]), "=f"(o[1]) : "l"(s01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o[2]), "=f"(o[3]) : "l"(s23));
         *reinterpret_cast<float4*>(&s_row[ly][4 * c]) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
@@ -1339,12 +1354,16 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
         uint8_t* out = ef_ws(p, frame, L.blur_off);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned long long sxy = 0ull, szw = 0ull;     // (x, y) and (z, w) columns advance together
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                sum.x = fmaf(r[j + k].x, taps[k], sum.x); sum.y = fmaf(r[j + k].y, taps[k], sum.y);
-                sum.z = fmaf(r[j + k].z, taps[k], sum.z); sum.w = fmaf(r[j + k].w, taps[k], sum.w);
+                const unsigned long long tk = ef_pack2(taps[k], taps[k]);
+                sxy = ef_fma2(ef_pack2(r[j + k].x, r[j + k].y), tk, sxy);
+                szw = ef_fma2(ef_pack2(r[j + k].z, r[j + k].w), tk, szw);
             }
+            float4 sum;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sum.x), "=f"(sum.y) : "l"(sxy));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sum.z), "=f"(sum.w) : "l"(szw));
             const int gy = y0 + 4 * rg + j;
             if (gy < L.h && gx < L.w) {
                 const unsigned packed = ef_sat_u8_rne(sum.x) | (ef_sat_u8_rne(sum.y) << 8) | (ef_sat_u8_rne(sum.z) << 16) | (ef_sat_u8_rne(sum.w) << 24);
