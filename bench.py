@@ -276,6 +276,20 @@ def main():
     roofline = with_traffic(roof(dom))
     roofline_pyr = with_traffic(roof("pyramid"))
     rooflines = {st: with_traffic(roof(st)) for st in per_call if per_call[st] > 0}
+    # What actually bounds these kernels: issue slots and the shared-memory pipe.  Executed warp instructions
+    # and shared-memory wavefronts per launch group come from the committed ncu capture (profiles/traffic.json), the time from
+    # this run; peak = 4 warp instructions resp. 1 wavefront per SM and clock at the SM clock sampled under load.
+    stage_issue, stage_smem = {}, {}
+    if clocks and clocks.get("sm_mhz") and tr.get("_frames"):
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk_per_ms = n_sm * float(clocks["sm_mhz"]) * 1e3
+        for st, t_ms in per_call.items():
+            key = "describe_bad" if (st == "describe" and dtype_id < 2) else st
+            scale = B / float(tr["_frames"])
+            if t_ms > 0 and key in tr.get("_warp_inst", {}):
+                stage_issue[st] = round(tr["_warp_inst"][key] * scale / (4.0 * clk_per_ms * t_ms), 4)
+            if t_ms > 0 and key in tr.get("_smem_wavefronts", {}):
+                stage_smem[st] = round(tr["_smem_wavefronts"][key] * scale / (clk_per_ms * t_ms), 4)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -289,7 +303,8 @@ def main():
             "data": "synthetic", "config": config, "frames_per_s": value * 1e6 / (W * H), "keypoints_per_s": kps,
             "keypoints_per_frame": n_frame, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_pyramid": roofline_pyr, "stage_ms_per_step": per_call,
-            "stage_roofline_frac": {k: round(v["frac"], 5) for k, v in rooflines.items()}, "cpu_baseline": cpu_baseline}
+            "stage_roofline_frac": {k: round(v["frac"], 5) for k, v in rooflines.items()},
+            "stage_issue_frac": stage_issue, "stage_smem_pipe_frac": stage_smem, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -25,10 +25,12 @@
 #include "ef_libm_f32.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 #define EF_SIFT_WARPS 2                 // per CTA: 4 keypoints
 #define EF_SIFT_KP_PER_CTA (2 * EF_SIFT_WARPS)
 #define EF_SIFT_REC 916                 // floats per record array (30x30 skewed needs 906)
+#define EF_SIFT_ZERO 908                // spare record slot (skewed 30x30 indices end at 905) holding an all-zero record
 #define EF_SIFT_BLK (2 * EF_SIFT_REC)   // record block of one keypoint (16-byte multiple): magnitudes then fractions
 #define EF_SIFT_WIN 48                  // staged window edge (pixels); every sample of a size-31 patch lies in [k-22, k+22]
 #define EF_SIFT_WIN_PITCH 136           // bytes per staged row: 64 pixels (48 + up to 15 alignment bytes), TWO bytes each -- entry x holds
@@ -68,7 +70,7 @@ __device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
 
 // All 32 lanes call this; lanes 0-15 work on keypoint slot 0 of the warp, lanes 16-31 on slot 1.
 // STAGED: integer keypoint, size 31, scale 1 (detectAndCompute path): window staging; image base and pitch 16-byte aligned.
-template <bool STAGED>
+template <bool STAGED, int V = 0>
 __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img, int w, int h, int pitch,
                                                 float kx, float ky, float size, float angle, float croppingScale,
                                                 const EfHashSiftTables& t, EfSiftWarpSmem& sm, uint8_t* out128, bool store)
@@ -184,6 +186,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         }
     }
     for (int b = 0; b < 9; b++) sm.hist[b * 32 + lane] = 0.f;
+    // all-zero record (magnitude +0, fraction 0, bin 0) in a spare slot: what the out-of-patch visits of the border cells read
+    if (hl == 0) { sm.rec[k][k + EF_SIFT_ZERO] = 0.f; sm.rec[k][EF_SIFT_REC + k + EF_SIFT_ZERO] = 0.f; }
     __syncwarp();
     // ---- trilinear histogram (hash_sift.cpp:233-290); cell (rb, cb) in 1..4
     {
@@ -192,12 +196,15 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const unsigned* __restrict__ op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
         float* __restrict__ hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
-        // Out-of-patch visits (rows/columns outside 0..29 for the border cells) are not branched around: they read record 0 and
-        // add +0.0f, which leaves every (non-negative) accumulator unchanged -- the warp executes the iteration anyway.
-        // Per patch row: first the 16 shares (loads + arithmetic, independent -> pipelined), then the 16 ordered read-modify-writes.
+        // Out-of-patch visits (rows/columns outside 0..29 for the border cells) are not branched around: they read the all-zero
+        // record and add +0.0f, which leaves every (non-negative) accumulator unchanged -- the warp executes the iteration anyway.
+        // Visits whose weight is exactly zero for EVERY cell are skipped (they too would only add +0.0f): the first row of the
+        // first row segment (row weight 0/8) and the first column of the first column segment (column weight 0/8) -- 31 of the
+        // 256 visits of a cell.
+        // Per patch row: first the 15 or 16 shares (loads + arithmetic, independent -> pipelined), then the ordered read-modify-writes.
 #pragma unroll
         for (int rseg = 0; rseg < 2; rseg++) {
-            for (int iy = 0; iy < 8; iy++) {
+            for (int iy = (rseg == 0 && (V & 2)) ? 1 : 0; iy < 8; iy++) {
                 const int y = 8 * (rb - 2 + rseg) + 3 + iy;
                 const bool rowok = (unsigned)y < 30u;
                 const float rf = 0.125f * (float)iy;
@@ -205,13 +212,13 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 float vo0[16], vo1[16];
                 unsigned hoff[16];
 #pragma unroll
-                for (int xo = 0; xo < 16; xo++) {
+                for (int xo = (V & 2) ? 1 : 0; xo < 16; xo++) {
                     const int cseg = xo >> 3, ix = xo & 7;
                     const bool ok = rowok && (unsigned)(xb + xo) < 30u;
-                    const int idx = ok ? rowidx + xo : 0;
+                    const int idx = ok ? rowidx + xo : ((V & 1) ? EF_SIFT_ZERO : 0);
                     const float mg = mp[idx];
                     const unsigned ob = op[idx];
-                    const float mag = ok ? fabsf(mg) : 0.f;
+                    const float mag = (V & 1) ? fabsf(mg) : (ok ? fabsf(mg) : 0.f);
                     hoff[xo] = ((ob >> 30) | ((__float_as_uint(mg) >> 31) << 2)) * 32u;
                     const float of = __uint_as_float(ob & 0x3fffffffu);
                     // distribute(): v1 = w*v; v0 = v - v1   (hash_sift.cpp:193-198)
@@ -223,7 +230,7 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                     vo0[xo] = vc - vo1[xo];
                 }
 #pragma unroll
-                for (int xo = 0; xo < 16; xo++) {
+                for (int xo = (V & 2) ? 1 : 0; xo < 16; xo++) {
                     float* h0 = hc + hoff[xo];
                     const float a0 = h0[0], a1 = h0[32];
                     h0[0] = a0 + vo0[xo];
@@ -281,6 +288,7 @@ void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTabl
     EF_COUNT_LAUNCH(1);
 }
 
+template <int V>
 __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_pipe_kernel(const __grid_constant__ EfPipe p, const EfHashSiftTables t, uint8_t* __restrict__ sift128)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_pipe_kernel(co
     }
     const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
     // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
-    ef_hashsift_one<true>(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],
+    ef_hashsift_one<true, V>(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],
                           sift128 + ((size_t)frame * p.nfeatures + offset + ii) * 128, valid);
 }
 
@@ -317,6 +325,13 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 {
     if (p.total_sift_blocks <= 0) return;
     const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
-    ef_hashsift_pipe_kernel<<<dim3(ef_div_up(p.total_sift_blocks, p.shard_n), p.nframes), EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128);
+    static const int variant = getenv("EF_SIFT_V") ? atoi(getenv("EF_SIFT_V")) : 3;
+    const dim3 grid(ef_div_up(p.total_sift_blocks, p.shard_n), p.nframes);
+    switch (variant) {
+    case 0: ef_hashsift_pipe_kernel<0><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    case 1: ef_hashsift_pipe_kernel<1><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    case 2: ef_hashsift_pipe_kernel<2><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    default: ef_hashsift_pipe_kernel<3><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    }
     EF_COUNT_LAUNCH(1);
 }

@@ -38,7 +38,7 @@ def main():
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     print("# " + " | ".join(["kernel", "grid"] + [c[1] for c in COLS]))
-    traffic = {}
+    traffic, winst, wavef = {}, {}, {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0]
         if name.startswith("void "):
@@ -55,12 +55,20 @@ def main():
                 b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
                     to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
                 traffic.setdefault(stage, []).append(b)
+                if "smsp__inst_executed.sum" in idx:
+                    winst.setdefault(stage, []).append(float(r[idx["smsp__inst_executed.sum"]]))
+                if "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum" in idx:
+                    wavef.setdefault(stage, []).append(float(r[idx["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]]))
                 break
     if traffic_path:
         # pyramid = 7 launches per step (sum); other stages = one launch per step (mean over the captured launches)
         res = {}
         for stage, v in traffic.items():
             res[stage] = sum(v) if stage == "pyramid" else sum(v) / len(v)
+        # executed warp instructions and shared-memory wavefronts per launch group: bench.py turns them into issue-slot and
+        # shared-memory-pipe fractions with its own live timing (the bounds that matter for these kernels)
+        res["_warp_inst"] = {st: (sum(v) if st == "pyramid" else sum(v) / len(v)) for st, v in winst.items()}
+        res["_smem_wavefronts"] = {st: (sum(v) if st == "pyramid" else sum(v) / len(v)) for st, v in wavef.items()}
         res["_frames"] = int(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 8
         res["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch group (one step of the captured bench command, _frames frames), from " + rep
         with open(traffic_path, "w") as f:
