@@ -162,10 +162,11 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     {
         float* __restrict__ magp = sm.rec[k] + k;
         float* __restrict__ ofp = sm.rec[k] + EF_SIFT_REC + k;
-        for (int i0 = hl; i0 < 900; i0 += 16 * 8) {
-            int tix[8], rix[8], pix[8];
+        constexpr int GB = 8;   // gathers in flight per lane (16: +0.3 %, measured)
+        for (int i0 = hl; i0 < 900; i0 += 16 * GB) {
+            int tix[GB], rix[GB], pix[GB];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < GB; u++) {
                 const int i = min(i0 + 16 * u, 899);          // lanes past the end repeat pixel 899 (their writes are skipped)
                 const int y = (i * 1093) >> 15, x = i - 30 * y; // i / 30 for i < 1024
                 const uint8_t* c = patch + (y + 1) * 32 + x + 1;
@@ -175,12 +176,12 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 rix[u] = i + 2 * (y >> 3);
                 pix[u] = i;
             }
-            float2 e[8];
-            float ew[8];
+            float2 e[GB];
+            float ew[GB];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { e[u] = __ldg(t.grad_table + tix[u]); ew[u] = __ldg(t.exp_table + pix[u]); }
+            for (int u = 0; u < GB; u++) { e[u] = __ldg(t.grad_table + tix[u]); ew[u] = __ldg(t.exp_table + pix[u]); }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < GB; u++) {
                 if (i0 + 16 * u < 900) { magp[rix[u]] = ew[u] * e[u].x; ofp[rix[u]] = e[u].y; }
             }
         }
