@@ -76,31 +76,7 @@ __global__ void __launch_bounds__(256) ef_resize_kernel(const __grid_constant__ 
 #define RS_TH 32
 #define RS_RWP 160
 #define RS_RH 43
-__device__ __forceinline__ unsigned long long ef_pack2(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ unsigned long long ef_mul2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long ef_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
 
-__device__ __forceinline__ unsigned long long ef_add2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 
 __global__ void __launch_bounds__(256) ef_resize_tiled_kernel(const __grid_constant__ EfPipe p, const int level)
 {

@@ -152,7 +152,41 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 patch[y * 32 + hl + 16 * xx] = dstVal; \
             } \
         }
-        if (inside) { EF_SIFT_SAMPLE_ROWS(false) } else { EF_SIFT_SAMPLE_ROWS(true) }
+        if (inside && STAGED && (V & 4)) {
+            // both samples of a lane and row (columns hl and hl + 16) advance together in packed fp32: the same operations in the
+            // same order as the scalar form above (separate multiplies and adds: the CPU reference is built without FMA)
+            const unsigned long long cx2 = ef_pack2(cx0, cx1), cy2 = ef_pack2(cy0, cy1);
+            const unsigned long long m02 = ef_pack2(M02, M02), m12 = ef_pack2(M12, M12), one2 = ef_pack2(1.f, 1.f), half2 = ef_pack2(0.5f, 0.5f);
+            const float nz = __uint_as_float(0x80000000u | (blockDim.z - 1u));   // -0.0f at run time (blockDim.z == 1), opaque to the compiler
+            const unsigned long long nz2 = ef_pack2(nz, nz);
+#pragma unroll 4
+            for (int y = 0; y < 32; y++) {
+                const float ru = M01 * (float)y, rv = M11 * (float)y;
+                const unsigned long long u2 = ef_add2(ef_add2(cx2, ef_pack2(ru, ru)), m02);
+                const unsigned long long v2 = ef_add2(ef_add2(cy2, ef_pack2(rv, rv)), m12);
+                float ua, ub, va, vb;
+                ef_unpack2(u2, ua, ub); ef_unpack2(v2, va, vb);
+                const int uia = (int)floorf(ua), uib = (int)floorf(ub), via = (int)floorf(va), vib = (int)floorf(vb);
+                const unsigned long long du2 = ef_sub2(u2, ef_pack2((float)uia, (float)uib)), dv2 = ef_sub2(v2, ef_pack2((float)via, (float)vib));
+                const unsigned long long omdu2 = ef_sub2(one2, du2), omdv2 = ef_sub2(one2, dv2);
+                const unsigned short* __restrict__ qa = reinterpret_cast<const unsigned short*>(base + (via - oy) * EF_SIFT_WIN_PITCH) + (uia - ox);
+                const unsigned short* __restrict__ qb = reinterpret_cast<const unsigned short*>(base + (vib - oy) * EF_SIFT_WIN_PITCH) + (uib - ox);
+                const unsigned a0 = qa[0], a1 = qa[EF_SIFT_WIN_PITCH / 2], b0 = qb[0], b1 = qb[EF_SIFT_WIN_PITCH / 2];
+                const unsigned long long q00 = ef_pack2((float)(a0 & 0xffu), (float)(b0 & 0xffu)), q01 = ef_pack2((float)(a0 >> 8), (float)(b0 >> 8));
+                const unsigned long long q10 = ef_pack2((float)(a1 & 0xffu), (float)(b1 & 0xffu)), q11 = ef_pack2((float)(a1 >> 8), (float)(b1 >> 8));
+                // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (seen in SASS); the reference rounds every
+                // product.  So each product is an FMA with a -0.0 addend that the compiler cannot see (x*y + -0.0 == round(x*y) bit for
+                // bit), and an FMA followed by an add is not fusable.
+                const unsigned long long tmp0 = ef_add2(ef_fma2(omdu2, q00, nz2), ef_fma2(du2, q01, nz2));
+                const unsigned long long tmp1 = ef_add2(ef_fma2(omdu2, q10, nz2), ef_fma2(du2, q11, nz2));
+                const unsigned long long tmp2 = ef_add2(ef_fma2(omdv2, tmp0, nz2), ef_fma2(dv2, tmp1, nz2));
+                float ra, rb;
+                ef_unpack2(ef_add2(tmp2, half2), ra, rb);
+                patch[y * 32 + hl] = (uint8_t)min(__float2int_rz(ra), 255);
+                patch[y * 32 + hl + 16] = (uint8_t)min(__float2int_rz(rb), 255);
+            }
+        }
+        else if (inside) { EF_SIFT_SAMPLE_ROWS(false) } else { EF_SIFT_SAMPLE_ROWS(true) }
 #undef EF_SIFT_SAMPLE_ROWS
     }
     __syncwarp();
@@ -326,13 +360,14 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 {
     if (p.total_sift_blocks <= 0) return;
     const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
-    static const int variant = getenv("EF_SIFT_V") ? atoi(getenv("EF_SIFT_V")) : 3;
+    static const int variant = getenv("EF_SIFT_V") ? atoi(getenv("EF_SIFT_V")) : 7;
     const dim3 grid(ef_div_up(p.total_sift_blocks, p.shard_n), p.nframes);
     switch (variant) {
     case 0: ef_hashsift_pipe_kernel<0><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     case 1: ef_hashsift_pipe_kernel<1><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     case 2: ef_hashsift_pipe_kernel<2><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
-    default: ef_hashsift_pipe_kernel<3><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    case 3: ef_hashsift_pipe_kernel<3><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    default: ef_hashsift_pipe_kernel<7><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     }
     EF_COUNT_LAUNCH(1);
 }
