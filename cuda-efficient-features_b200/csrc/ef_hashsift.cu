@@ -231,6 +231,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const unsigned* __restrict__ op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
         float* __restrict__ hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
+        const float nzh = __uint_as_float(0x80000000u | (blockDim.z - 1u));   // -0.0f at run time, opaque to the compiler
+        const unsigned long long nzh2 = ef_pack2(nzh, nzh);
         // Out-of-patch visits (rows/columns outside 0..29 for the border cells) are not branched around: they read the all-zero
         // record and add +0.0f, which leaves every (non-negative) accumulator unchanged -- the warp executes the iteration anyway.
         // Visits whose weight is exactly zero for EVERY cell are skipped (they too would only add +0.0f): the first row of the
@@ -246,6 +248,52 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 const int rowidx = y * 30 + 2 * (y >> 3) + xb;
                 float vo0[16], vo1[16];
                 unsigned hoff[16];
+                if (V & 8) {
+                    // packed fp32 shares: visits (xo, xo + 1) of one column segment advance together.  The sign bit of the magnitude record
+                    // (bin bit 2) is carried through instead of cleared -- every operation below is sign-symmetric -- and dropped by
+                    // the |.| of the final additions.  Products are FMAs with the run-time -0.0 addend (see the sampling loop).
+                    float mgv[16];
+                    unsigned ofv[16];
+#pragma unroll
+                    for (int xo = 1; xo < 16; xo++) {
+                        const bool ok = rowok && (unsigned)(xb + xo) < 30u;
+                        const int idx = ok ? rowidx + xo : EF_SIFT_ZERO;
+                        mgv[xo] = mp[idx];
+                        const unsigned ob = op[idx];
+                        hoff[xo] = ((ob >> 30) | ((__float_as_uint(mgv[xo]) >> 31) << 2)) * 32u;
+                        ofv[xo] = ob & 0x3fffffffu;
+                    }
+                    {   // xo = 1 (column weight 1/8 of the first segment) has no partner
+                        const float v1 = rf * mgv[1];
+                        const float vr = rseg == 0 ? v1 : mgv[1] - v1;
+                        const float vc = 0.125f * vr;
+                        vo1[1] = __uint_as_float(ofv[1]) * vc;
+                        vo0[1] = vc - vo1[1];
+                    }
+                    const unsigned long long rf2 = ef_pack2(rf, rf);
+#pragma unroll
+                    for (int xp = 2; xp < 16; xp += 2) {
+                        const int cseg = xp >> 3, ix = xp & 7;
+                        const unsigned long long mg2 = ef_pack2(mgv[xp], mgv[xp + 1]);
+                        const unsigned long long of2 = ef_pack2(__uint_as_float(ofv[xp]), __uint_as_float(ofv[xp + 1]));
+                        const unsigned long long v1 = ef_fma2(rf2, mg2, nzh2);
+                        const unsigned long long vr = rseg == 0 ? v1 : ef_sub2(mg2, v1);
+                        const unsigned long long c1 = ef_fma2(ef_pack2(0.125f * (float)ix, 0.125f * (float)(ix + 1)), vr, nzh2);
+                        const unsigned long long vc = cseg == 0 ? c1 : ef_sub2(vr, c1);
+                        const unsigned long long o1 = ef_fma2(of2, vc, nzh2);
+                        const unsigned long long o0 = ef_sub2(vc, o1);
+                        ef_unpack2(o1, vo1[xp], vo1[xp + 1]);
+                        ef_unpack2(o0, vo0[xp], vo0[xp + 1]);
+                    }
+#pragma unroll
+                    for (int xo = 1; xo < 16; xo++) {
+                        float* h0 = hc + hoff[xo];
+                        const float a0 = h0[0], a1 = h0[32];
+                        h0[0] = a0 + fabsf(vo0[xo]);
+                        h0[32] = a1 + fabsf(vo1[xo]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int xo = (V & 2) ? 1 : 0; xo < 16; xo++) {
                     const int cseg = xo >> 3, ix = xo & 7;
@@ -360,14 +408,15 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 {
     if (p.total_sift_blocks <= 0) return;
     const size_t smem = sizeof(EfSiftWarpSmem) * EF_SIFT_WARPS;
-    static const int variant = getenv("EF_SIFT_V") ? atoi(getenv("EF_SIFT_V")) : 7;
+    static const int variant = getenv("EF_SIFT_V") ? atoi(getenv("EF_SIFT_V")) : 15;
     const dim3 grid(ef_div_up(p.total_sift_blocks, p.shard_n), p.nframes);
     switch (variant) {
     case 0: ef_hashsift_pipe_kernel<0><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     case 1: ef_hashsift_pipe_kernel<1><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     case 2: ef_hashsift_pipe_kernel<2><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     case 3: ef_hashsift_pipe_kernel<3><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
-    default: ef_hashsift_pipe_kernel<7><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    case 7: ef_hashsift_pipe_kernel<7><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
+    default: ef_hashsift_pipe_kernel<15><<<grid, EF_SIFT_WARPS * 32, smem, s>>>(p, t, sift128); break;
     }
     EF_COUNT_LAUNCH(1);
 }
