@@ -400,7 +400,7 @@ __device__ __forceinline__ unsigned ef_arc9x2(unsigned m)
     return r & __byte_perm(m, 0, 0x2301);
 }
 
-__global__ void __launch_bounds__(256) ef_score_kernel(const __grid_constant__ EfPipe p)
+__global__ void __launch_bounds__(256, 8) ef_score_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ __align__(16) unsigned s_h0[SC_ROWS][SC_HW];
     __shared__ __align__(16) unsigned s_h1[SC_ROWS][SC_HW];
@@ -686,7 +686,7 @@ __device__ __forceinline__ bool ef_nms_scan_block(const float* __restrict__ resp
 // TB, TK: block edge and block reach of the disc as compile-time constants (8, 2 for the default radius 15: no runtime divisions,
 // unrolled neighbour walk); TB = 0: taken from the parameter block (any radius).
 template <int TB, int TK>
-__global__ void __launch_bounds__(256) ef_nms_kernel(const __grid_constant__ EfPipe p)
+__global__ void __launch_bounds__(256, 8) ef_nms_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ unsigned s_mask[EF_NMS_RT * EF_TILE];
     __shared__ EfBlockMax s_blk[EF_NMS_MAX_BLK];
@@ -1152,7 +1152,7 @@ void ef_launch_select(const EfPipe& p, cudaStream_t s)
 #define EF_KPTS_PER_CTA 8
 __constant__ int c_umax[16] = { 15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3 };
 
-__global__ void __launch_bounds__(256) ef_angle_pack_kernel(const __grid_constant__ EfPipe p)
+__global__ void __launch_bounds__(256, 8) ef_angle_pack_kernel(const __grid_constant__ EfPipe p)
 {
     __shared__ int s_m[EF_KPTS_PER_CTA][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
