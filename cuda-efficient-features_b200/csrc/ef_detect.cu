@@ -347,8 +347,14 @@ void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
     for (int l = 1; l < p.nlevels; l++) {
         const bool src16 = l > 1 || ((reinterpret_cast<uintptr_t>(p.img0) | p.img0_stride | (unsigned long long)p.img0_pitch) & 15ull) == 0;
         if (src16 && p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.22f && !g_ef_resize_legacy) {
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(ef_resize_tiled16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS3_SMEM); attr_set = true; }
+            // the attribute is per device (ef_mg_* drives several devices from one process): one bit per device
+            static unsigned long long configured = 0;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!((__atomic_load_n(&configured, __ATOMIC_RELAXED) >> (dev & 63)) & 1ull)) {
+                cudaFuncSetAttribute(ef_resize_tiled16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS3_SMEM);
+                __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
+            }
             const dim3 grid(ef_div_up(p.lv[l].w, RS3_TW), ef_div_up(p.lv[l].h, RS3_TH), p.nframes);
             ef_resize_tiled16_kernel<<<grid, 256, RS3_SMEM, s>>>(p, l);
         } else if (p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.25f) {
