@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_flat_kernel(co
     const bool valid = i < job.n;
     const int ii = valid ? i : first;
     const float4 k = job.kpts[ii];
-    ef_hashsift_one<STAGED, 3>(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)ii * 128, valid);
+    ef_hashsift_one<STAGED, 15>(job.img, job.w, job.h, job.pitch, k.x, k.y, k.z, k.w, job.scale, t, sm[warp], sift128 + (size_t)ii * 128, valid);
 }
 
 void ef_launch_hashsift_features_flat(const EfDescJob& job, const EfHashSiftTables& t, uint8_t* sift128, cudaStream_t s)
