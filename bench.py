@@ -126,6 +126,8 @@ def main():
                          "rank 0, all-gather of the band candidates and MAX all-reduce of the descriptors inside the timed region; strong scaling")
     args = ap.parse_args()
 
+    # NCCL's own log lines (e.g. "NCCL version ..." when the box sets NCCL_DEBUG) go to stderr: stdout carries the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
