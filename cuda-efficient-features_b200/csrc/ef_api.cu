@@ -484,6 +484,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
         L.rowcnt_off = q.rowcnt_off; L.surv_off = q.surv_off; L.sel_off = q.sel_off;
         L.tile_start = tiles; L.blur_tile_start = btiles; L.band_start = bands; L.kpt_block_start = kblocks; L.sift_block_start = sblocks;
         L.strips_x = ef_div_up(L.tiles_x, 4); L.strip_start = strips;
+        L.tiles_x_inv = 0xffffffffu / (unsigned)L.tiles_x; L.strips_x_inv = 0xffffffffu / (unsigned)L.strips_x; L.blur_tiles_x_inv = 0xffffffffu / (unsigned)L.blur_tiles_x;
         if (l >= p.first_level) {
             tiles += L.tiles_x * L.score_rows;
             strips += L.strips_x * L.own_rows;

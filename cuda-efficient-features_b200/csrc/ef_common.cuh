@@ -33,6 +33,7 @@ struct EfLevel {
     int blur_pitch;     // bytes
     int resp_pitch;     // floats
     int tiles_x, tiles_y;
+    unsigned tiles_x_inv, strips_x_inv, blur_tiles_x_inv; // floor((2^32 - 1) / d) of tiles_x, strips_x, blur_tiles_x: ef_div_fast()
     // tile rows this call works on (whole level unless the frame is cut into bands over several GPUs, ef_band_*):
     // the score stage covers rows [score_ty0, score_ty0 + score_rows) = the owned rows plus the NMS halo,
     // NMS / compaction the owned rows [own_ty0, own_ty0 + own_rows)
@@ -136,6 +137,13 @@ __device__ __forceinline__ unsigned long long ef_sub2(unsigned long long a, unsi
     unsigned long long r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
+}
+// t / d for 0 <= t < 2^31, d >= 1, inv = floor((2^32 - 1) / d): the estimate umulhi(t, inv) is q or q - 1
+__device__ __forceinline__ int ef_div_fast(int t, int d, unsigned inv)
+{
+    unsigned q = __umulhi((unsigned)t, inv);
+    if ((unsigned)t - q * (unsigned)d >= (unsigned)d) q++;
+    return (int)q;
 }
 // order-preserving map float -> uint32 (larger float <=> larger key)
 __device__ __forceinline__ unsigned ef_float_key(float f)

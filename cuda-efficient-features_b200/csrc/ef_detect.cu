@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256, 8) ef_score_kernel(const __grid_constant_
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.tile_start;
-    const int tyl = t / L.tiles_x, ty = tyl + L.score_ty0;
+    const int tyl = ef_div_fast(t, L.tiles_x, L.tiles_x_inv), ty = tyl + L.score_ty0;
     const int x0 = (t - tyl * L.tiles_x) * EF_TILE, y0 = ty * EF_TILE;
 
     int pitch;
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256, 8) ef_nms_kernel(const __grid_constant__ 
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::strip_start);
     const EfLevel& L = p.lv[level];
     const int s = blockIdx.x - L.strip_start;
-    const int tyl = s / L.strips_x, ty = tyl + L.own_ty0, tx0 = (s - tyl * L.strips_x) * EF_NMS_RT;
+    const int tyl = ef_div_fast(s, L.strips_x, L.strips_x_inv), ty = tyl + L.own_ty0, tx0 = (s - tyl * L.strips_x) * EF_NMS_RT;
     const int ntx = min(EF_NMS_RT, L.tiles_x - tx0);
     const int x0 = tx0 * EF_TILE, y0 = ty * EF_TILE;
     const float* __restrict__ resp = reinterpret_cast<const float*>(ef_ws(p, frame, L.resp_off));
@@ -1275,7 +1275,7 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     const int level = ef_find_level(p, blockIdx.x, &EfLevel::blur_tile_start);
     const EfLevel& L = p.lv[level];
     const int t = blockIdx.x - L.blur_tile_start;
-    const int tyl = t / L.blur_tiles_x, tyi = tyl + L.blur_ty0;
+    const int tyl = ef_div_fast(t, L.blur_tiles_x, L.blur_tiles_x_inv), tyi = tyl + L.blur_ty0;
     const int x0 = (t - tyl * L.blur_tiles_x) * BL_TW, y0 = tyi * BL_TH;
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
