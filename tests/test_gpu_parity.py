@@ -205,6 +205,41 @@ def test_full_size_4k_matches_oracle(torch_cuda, oracle, dtype_name):
     assert np.array_equal(gd[go], od[oo])
 
 
+@pytest.mark.parametrize("dtype_name", ["HASH_SIFT_512", "BAD_512"])
+def test_full_size_8k_matches_oracle(torch_cuda, oracle, dtype_name):
+    """BASELINE.json configs[3]: 7680x4320, 40 000 keypoints, against the oracle (1-2 s on 16 host threads).  The only
+    configuration where EVERY per-level quota binds (the radix select cuts each level) and where a full-frame int32 integral
+    would wrap (7680 * 4320 * 255 > 2^31): keypoints and descriptor bytes identical.  The compute-only BAD path
+    (vector<KeyPoint>, full-frame integral image like the reference's cv::integral) is checked on the same frame."""
+    import efb200, efo
+    torch = torch_cuda
+    w, h, nfeat = 7680, 4320, 40000
+    img = oracle.synth_frame(util.SEED + 43, 0, w, h)
+    ef = make_ef(nfeatures=nfeat, dtype=getattr(efb200, dtype_name), max_width=w, max_height=h)
+    d_img = torch.from_numpy(img).cuda()
+    kp, desc = ef.detectAndComputeAsync(d_img)
+    g = ef.convert(kp)
+    gd = desc.cpu().numpy()
+    ok, od, _ = oracle.detect_and_compute(img, oracle.make_params(nfeatures=nfeat, desc_type=getattr(efo, dtype_name)))
+    o = util.oracle_to_struct(ok)
+    assert len(o) == nfeat, f"8K noise must fill every quota, oracle delivers {len(o)}"
+    util.assert_keypoints_equal(g, o)
+    _, go = util.canon_keypoints(g)
+    _, oo = util.canon_keypoints(o)
+    diff = gd[go] != od[oo]
+    assert diff.sum() == 0, f"{dtype_name}@8K: {diff.any(axis=1).sum()} of {len(g)} descriptors differ"
+    del ef
+    if dtype_name == "BAD_512":
+        # compute-only on the level-0 image: keypoints near the bottom-right corner see wrapped int32 prefix sums
+        k = np.stack([g["x"], g["y"], g["size"], g["angle"]], axis=1).astype(np.float32)[:20000]
+        k = np.concatenate([k, efo.stress_keypoints(w, h, 6000, seed=13)])
+        k[-3000:, 0] = np.minimum(k[-3000:, 0] * 0.05 + (w - 400), w - 1)       # bottom-right 400 x 250 px block
+        k[-3000:, 1] = np.minimum(k[-3000:, 1] * 0.05 + (h - 250), h - 1)
+        gb = efb200.BAD.create(1.0, 100, max_width=w, max_height=h, max_keypoints=len(k)).compute(img, k)
+        ob = oracle.bad(img, k, 1.0, 512)
+        assert np.array_equal(gb, ob), f"compute-only BAD-512 at 8K: {(gb != ob).any(axis=1).sum()} of {len(k)} descriptors differ"
+
+
 def nms_property_ok(k, radius, scales):
     """no two keypoints of the same level closer than the radius in level coordinates (checked on the scaled coordinates with the
     rounding slack of scalePoints: |x' - s x| < 1)"""
