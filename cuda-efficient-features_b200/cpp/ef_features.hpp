@@ -27,7 +27,7 @@ struct MatView { void* data = nullptr; size_t step = 0; int rows = 0, cols = 0; 
 // cv::KeyPoint fields filled by convert() (cuda_efficient_features.cpp:323-349)
 struct KeyPoint { float x, y, size, angle, response; int octave; };
 
-struct Capacity { int max_width = 3840, max_height = 2160, max_batch = 1, max_keypoints = 0, device = 0; };
+struct Capacity { int max_width = 3840, max_height = 2160, max_batch = 1, max_keypoints = 0, device = 0, flags = 0; };
 
 class EfficientFeatures
 {
@@ -45,7 +45,7 @@ public:
         p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels; p.first_level = firstLevel;
         p.fast_threshold = fastThreshold; p.nonmax_radius = nonmaxRadius; p.desc_type = dtype;
         p.max_width = cap.max_width; p.max_height = cap.max_height; p.max_batch = cap.max_batch;
-        p.max_keypoints = cap.max_keypoints; p.device = cap.device;
+        p.max_keypoints = cap.max_keypoints; p.device = cap.device; p.flags = cap.flags;
         ef_handle* h = nullptr;
         const int rc = ef_create(&p, &h);
         if (rc != EF_OK) throw Error(rc, "ef_create failed (no CUDA device, bad argument or out of memory); there is no CPU fallback");
@@ -160,10 +160,11 @@ public:
 
 protected:
     Describer(EfficientFeatures::DescriptorType t, float scale, const Capacity& cap)
-        : ef_(EfficientFeatures::create(1, 1.2f, 8, 0, 20, 15, t, cap))
+        : ef_(EfficientFeatures::create(1, 1.2f, 8, 0, 20, 15, t, compute_only(cap)))   // tables + per-keypoint scratch only, like the reference describers
     {
         if (ef_set_param(ef_->handle(), EF_PARAM_DESC_SCALE, scale) != EF_OK) throw Error(EF_ERR_BAD_ARG, "bad scale");
     }
+    static Capacity compute_only(Capacity c) { c.flags |= EF_FLAG_COMPUTE_ONLY; return c; }
     std::unique_ptr<EfficientFeatures> ef_;
 };
 

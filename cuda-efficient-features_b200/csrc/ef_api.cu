@@ -182,6 +182,34 @@ int fail(ef_handle* h, int code, const std::string& msg)
             return fail(h, EF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
     } while (0)
 
+// Entry points run on the handle's device and leave the caller's current device as they found it (a single-process multi-GPU
+// caller -- PyTorch, ef_mg_* -- must not see its device change under its feet).
+struct DeviceGuard {
+    int prev = -1; bool switched = false, ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev) { ok = cudaSetDevice(dev) == cudaSuccess; switched = ok; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define EF_ON_DEVICE(h) DeviceGuard guard__((h)->device); if (!guard__.ok) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed")
+
+bool compute_only(const ef_handle* h) { return (h->prm.flags & EF_FLAG_COMPUTE_ONLY) != 0; }
+
+// sum of the per-level quotas: what the path can deliver at most (the last level takes max(nfeatures - sum, 0), so the sum can
+// exceed nfeatures by the rounding of the earlier levels, e.g. 8 for nfeatures = 7)
+int quota_sum(const ef_params& p)
+{
+    Geometry g;
+    compute_geometry(64, 64, p.scale_factor, p.nlevels, p.nfeatures, g);
+    int s = 0;
+    for (int l = 0; l < p.nlevels; l++) s += g.quota[l];
+    return s;
+}
+
 void free_all(ef_handle* h)
 {
     cudaFree(h->d_ws); cudaFree(h->d_counters);
@@ -214,6 +242,7 @@ int validate(const ef_params& p, std::string& why)
     if (p.desc_type < EF_BAD_256 || p.desc_type > EF_HASH_SIFT_512) { why = "unknown descriptor type"; return EF_ERR_BAD_ARG; }
     if (p.max_width < 32 || p.max_height < 32 || p.max_width > 32767 || p.max_height > 32767) { why = "max_width/max_height must be in [32,32767] (short2 locations)"; return EF_ERR_BAD_ARG; }
     if (p.max_batch < 1) { why = "max_batch must be >= 1"; return EF_ERR_BAD_ARG; }
+    if (p.flags & ~EF_FLAG_COMPUTE_ONLY) { why = "unknown bits in flags"; return EF_ERR_BAD_ARG; }
     return EF_OK;
 }
 
@@ -399,15 +428,22 @@ int allocate(ef_handle* h)
     plan_workspace(h);
     size_t total = 0;
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { total += bytes; return cudaMalloc(ptr, bytes ? bytes : 1); };
-    EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
-    // row padding (columns w .. pitch) is read by the 16-byte window loads but never written: define it once
-    EF_CUDA(h, cudaMemset(h->d_ws, 0, (size_t)h->slot_bytes * p.max_batch));
-    EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
-    h->sift_rows = std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
+    const bool conly = compute_only(h);
+    if (!conly) {
+        EF_CUDA(h, alloc((void**)&h->d_ws, (size_t)h->slot_bytes * p.max_batch));
+        // row padding (columns w .. pitch) is read by the 16-byte window loads but never written: define it once
+        EF_CUDA(h, cudaMemset(h->d_ws, 0, (size_t)h->slot_bytes * p.max_batch));
+        EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
+    }
+    h->sift_rows = conly ? (size_t)p.max_keypoints : std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
     EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
     EF_CUDA(h, alloc((void**)&h->d_integral, (size_t)(p.max_width + 1) * (p.max_height + 1) * 4));
     EF_CUDA(h, alloc((void**)&h->d_segsum, (size_t)(p.max_width + 1) * (ef_div_up(p.max_height, 64) + 1) * 4));
     EF_CUDA(h, alloc((void**)&h->d_kpts4, (size_t)p.max_keypoints * sizeof(float4)));
+    EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+    EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    if (conly) { h->total_bytes = total; return EF_OK; }
     // host-API staging
     h->in_pitch = ef_align_up(p.max_width, 128);
     h->in_stride = h->in_pitch * p.max_height;
@@ -422,9 +458,6 @@ int allocate(ef_handle* h)
     EF_CUDA(h, cudaMallocHost((void**)&h->h_counts_pinned, sizeof(int) * (p.max_batch + EF_MAX_LEVELS * 4)));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-    EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
-    EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     if (const char* e = std::getenv("EF_B200_OVERLAP_BLUR")) h->overlap_blur = std::atoi(e) != 0;   // 1: blur on the side stream (A/B switch)
     if (const char* e = std::getenv("EF_B200_HOST_CHUNK")) h->host_chunk = std::max(1, std::atoi(e)); // frames per pipeline chunk of the host API
     h->ev_in.resize(p.max_batch); h->ev_cnt.resize(p.max_batch);
@@ -441,6 +474,7 @@ int allocate(ef_handle* h)
 int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i = 0, int shard_n = 1)
 {
     const ef_params& p = h->prm;
+    if (compute_only(h)) return fail(h, EF_ERR_UNSUPPORTED, "the handle was created with EF_FLAG_COMPUTE_ONLY: no detection workspace");
     if (w > p.max_width || hh > p.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than max_width x max_height of the handle");
     if (nframes < 1 || nframes > p.max_batch) return fail(h, EF_ERR_CAPACITY, "nframes exceeds max_batch of the handle");
     if (w < 32 || hh < 32) return fail(h, EF_ERR_BAD_ARG, "image smaller than 32x32");
@@ -568,7 +602,7 @@ void ef_default_params(ef_params* p)
     // defaults of EfficientFeatures::create, include/cuda_efficient_features.h:47-48
     p->nfeatures = 5000; p->scale_factor = 1.2f; p->nlevels = 8; p->first_level = 0; p->fast_threshold = 20;
     p->nonmax_radius = 15; p->desc_type = EF_HASH_SIFT_256; p->desc_scale = 1.f;
-    p->max_width = 3840; p->max_height = 2160; p->max_batch = 1; p->max_keypoints = 0; p->device = 0;
+    p->max_width = 3840; p->max_height = 2160; p->max_batch = 1; p->max_keypoints = 0; p->device = 0; p->flags = 0;
 }
 
 int ef_create(const ef_params* params, ef_handle** out)
@@ -590,7 +624,8 @@ int ef_create(const ef_params* params, ef_handle** out)
         delete h; return EF_ERR_CUDA;
     }
     h->device = params->device;
-    if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return EF_ERR_CUDA; }
+    DeviceGuard guard(h->device);
+    if (!guard.ok) { delete h; return EF_ERR_CUDA; }
     rc = allocate(h);
     if (rc == EF_OK) rc = upload_tables(h);
     if (rc != EF_OK) { std::fprintf(stderr, "ef_create: %s\n", h->err.c_str()); free_all(h); delete h; return rc; }
@@ -601,7 +636,7 @@ int ef_create(const ef_params* params, ef_handle** out)
 void ef_destroy(ef_handle* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     free_all(h);
     delete h;
 }
@@ -627,20 +662,26 @@ int ef_set_param(ef_handle* h, int id, double value)
     const bool replan = q.nfeatures > h->prm.nfeatures || q.nlevels != h->prm.nlevels || q.scale_factor != h->prm.scale_factor ||
                         q.nonmax_radius != h->prm.nonmax_radius; // block-map and survivor-list capacities depend on the radius
     if (q.max_keypoints < q.nfeatures) q.max_keypoints = q.nfeatures;
-    h->prm = q;
-    if (replan) {
-        // capacities changed: re-plan and re-allocate here (setters are not on the hot path)
-        cudaSetDevice(h->device);
-        cudaDeviceSynchronize();
-        free_all(h);
-        const int dev = h->device; const bool keep = h->keep_proj;
-        *h = ef_handle();
-        h->prm = q; h->device = dev; h->keep_proj = keep;
-        rc = allocate(h);
-        if (rc == EF_OK) rc = upload_tables(h);
-        if (rc == EF_OK && h->keep_proj) rc = ef_debug_keep_projection(h, 1);
-        if (rc != EF_OK) return rc;
+    if (!replan) { h->prm = q; return EF_OK; }
+    // capacities changed (setters are not on the hot path): build the new resources FIRST and swap them in only when everything
+    // succeeded, so that a failure (e.g. out of memory after a large setMaxFeatures) leaves the handle exactly as it was
+    EF_ON_DEVICE(h);
+    cudaDeviceSynchronize();
+    ef_handle* n = new (std::nothrow) ef_handle();
+    if (!n) return fail(h, EF_ERR_CUDA, "out of host memory");
+    n->prm = q; n->device = h->device;
+    rc = allocate(n);
+    if (rc == EF_OK) rc = upload_tables(n);
+    if (rc == EF_OK && h->keep_proj) rc = ef_debug_keep_projection(n, 1);
+    if (rc != EF_OK) {
+        const std::string why2 = "re-planning the workspace failed, parameters unchanged: " + n->err;
+        free_all(n); delete n;
+        return fail(h, rc, why2);
     }
+    n->timing = h->timing; n->keep_proj = h->keep_proj; n->overlap_blur = h->overlap_blur; n->host_chunk = h->host_chunk;
+    free_all(h);
+    *h = *n;          // plain members and resource pointers; `n` owns nothing afterwards
+    delete n;
     return EF_OK;
 }
 
@@ -674,7 +715,7 @@ int ef_detect_and_compute_batch_async(ef_handle* h, int nframes, const uint8_t* 
     if (pitch < (size_t)width) return fail(h, EF_ERR_BAD_ARG, "pitch smaller than width");
     if (kpts_pitch < (size_t)h->prm.nfeatures * 4 || (kpts_pitch & 3)) return fail(h, EF_ERR_BAD_ARG, "kpts_pitch must be >= 4*nfeatures and a multiple of 4");
     if (d_desc && desc_pitch < (size_t)desc_bytes_of(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     EfPipe P;
     int rc = build_pipe(h, nframes, width, height, P);
     if (rc != EF_OK) return rc;
@@ -728,7 +769,7 @@ static int compute_check(ef_handle* h, const uint8_t* d_img, size_t pitch, int w
     if (width > h->prm.max_width || height > h->prm.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than the handle was created for");
     if (n > h->prm.max_keypoints) return fail(h, EF_ERR_CAPACITY, "more keypoints than max_keypoints of the handle");
     if (desc_pitch < (size_t)desc_bytes_of(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     return -1;
 }
 
@@ -757,7 +798,7 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     if (!h_imgs || !h_kpts5 || !h_counts) return fail(h, EF_ERR_BAD_ARG, "null host pointer");
     if (nframes < 1 || nframes > h->prm.max_batch) return fail(h, EF_ERR_CAPACITY, "nframes exceeds max_batch of the handle");
     if (width > h->prm.max_width || height > h->prm.max_height) return fail(h, EF_ERR_CAPACITY, "image larger than the handle was created for");
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     const int nf = h->prm.nfeatures, db = desc_bytes_of(h->prm.desc_type);
     // Chunked pipeline over three streams: the upload of chunk c+1 (getInputMat, cuda_efficient_features.cpp:71-77) and the
@@ -820,7 +861,8 @@ int ef_detect_and_compute_host(ef_handle* h, const uint8_t* h_img, size_t pitch,
 // ---- introspection ------------------------------------------------------------------------------
 size_t ef_band_candidate_bytes(const ef_handle* h)
 {
-    return h ? (size_t)ef_align_up((unsigned long long)EF_BAND_HDR + 8ull * (unsigned long long)h->prm.nfeatures, 16) : 0;
+    // the per-level lists are laid out by the prefix of the quotas, whose sum can exceed nfeatures (see quota_sum)
+    return h ? (size_t)ef_align_up((unsigned long long)EF_BAND_HDR + 8ull * (unsigned long long)std::max(quota_sum(h->prm), h->prm.nfeatures), 16) : 0;
 }
 
 int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
@@ -830,7 +872,7 @@ int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, cons
     if (!d_imgs || !d_cand) return fail(h, EF_ERR_BAD_ARG, "null image / candidate pointer");
     if (nshards < 1 || shard < 0 || shard >= nshards) return fail(h, EF_ERR_BAD_ARG, "shard must be in [0, nshards)");
     if (pitch < (size_t)width) return fail(h, EF_ERR_BAD_ARG, "pitch smaller than width");
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     EfPipe P;
     int rc = build_pipe(h, nframes, width, height, P, shard, nshards);
@@ -862,7 +904,7 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
     if (kpts_pitch < (size_t)h->prm.nfeatures * 4 || (kpts_pitch & 3)) return fail(h, EF_ERR_BAD_ARG, "kpts_pitch must be >= 4*nfeatures and a multiple of 4");
     const int db = desc_bytes_of(h->prm.desc_type);
     if (d_desc && desc_pitch < (size_t)db) return fail(h, EF_ERR_BAD_ARG, "desc_pitch smaller than the descriptor size");
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     EfPipe P;
     int rc = build_pipe(h, nframes, h->last_w, h->last_h, P, shard, nshards);
@@ -948,7 +990,7 @@ int ef_debug_project_async(ef_handle* h, const uint8_t* d_sift128, int n, int pa
     if (!h || !d_sift128 || !d_desc || n < 0 || path < 0 || path > 3) return EF_ERR_BAD_ARG;
     if (is_bad(h->prm.desc_type)) return fail(h, EF_ERR_BAD_ARG, "the handle's descriptor type is not HashSIFT");
     if (n == 0) return EF_OK;
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, EF_ERR_CUDA, "cudaSetDevice failed");
+    EF_ON_DEVICE(h);
     const int db = desc_bytes_of(h->prm.desc_type), v = db == 32 ? 0 : 1;
     const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
     g_ef_project_path = path;   // tests only: not thread safe

@@ -51,7 +51,10 @@ class ef_params(C.Structure):
     _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("first_level", C.c_int),
                 ("fast_threshold", C.c_int), ("nonmax_radius", C.c_int), ("desc_type", C.c_int), ("desc_scale", C.c_float),
                 ("max_width", C.c_int), ("max_height", C.c_int), ("max_batch", C.c_int), ("max_keypoints", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("flags", C.c_int)]
+
+
+FLAG_COMPUTE_ONLY = 1
 
 
 class ef_level_view(C.Structure):
@@ -138,10 +141,14 @@ def _desc_bytes(dtype: int) -> int:
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
 
 
-def _stream_ptr(stream) -> int:
+def _stream_ptr(stream, device=None) -> int:
+    """cudaStream_t of `stream`, or of torch's current stream ON `device` (the handle's / the tensors' device, which need
+    not be torch's current device in a single-process multi-GPU program)."""
     torch = _torch()
     if stream is None:
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
+    elif device is not None and stream.device != torch.device(device):
+        raise EfError(f"stream belongs to {stream.device}, the call runs on {device}")
     return int(stream.cuda_stream)
 
 
@@ -191,10 +198,12 @@ class _Handle:
         return out.value
 
 
-def _check_image_tensor(img):
+def _check_image_tensor(img, device=None):
     torch = _torch()
     if not (isinstance(img, torch.Tensor) and img.is_cuda and img.dtype == torch.uint8 and img.dim() == 2 and img.stride(1) == 1):
         raise EfError("image must be a 2-D uint8 CUDA tensor with unit column stride (CV_8UC1 GpuMat)")
+    if device is not None and img.device != device:
+        raise EfError(f"image lives on {img.device}, the object was created on {device} (one object per device)")
 
 
 class EfficientFeatures:
@@ -204,11 +213,11 @@ class EfficientFeatures:
     BAD_256, BAD_512, HASH_SIFT_256, HASH_SIFT_512 = 0, 1, 2, 3
 
     def __init__(self, nfeatures=5000, scaleFactor=1.2, nlevels=8, firstLevel=0, fastThreshold=20, nonmaxRadius=15,
-                 dtype=HASH_SIFT_256, max_width=3840, max_height=2160, max_batch=1, max_keypoints=0, device=-1):
+                 dtype=HASH_SIFT_256, max_width=3840, max_height=2160, max_batch=1, max_keypoints=0, device=-1, flags=0):
         self._h = _Handle(nfeatures=nfeatures, scale_factor=scaleFactor, nlevels=nlevels, first_level=firstLevel,
                           fast_threshold=fastThreshold, nonmax_radius=nonmaxRadius, desc_type=dtype,
                           max_width=max_width, max_height=max_height, max_batch=max_batch,
-                          max_keypoints=max_keypoints, device=device)
+                          max_keypoints=max_keypoints, device=device, flags=flags)
         self._out = None
 
     @staticmethod
@@ -235,7 +244,7 @@ class EfficientFeatures:
         dk = torch.from_numpy(k).to(self._h.device)
         desc = torch.empty((len(k), self.descriptorSize()), dtype=torch.uint8, device=self._h.device)
         self._h.check(self._h.L.ef_compute_async(self._h.h, dev_img.data_ptr(), dev_img.stride(0), dev_img.shape[1], dev_img.shape[0],
-                                                 dk.data_ptr(), len(k), desc.data_ptr(), desc.stride(0), _stream_ptr(None)))
+                                                 dk.data_ptr(), len(k), desc.data_ptr(), desc.stride(0), _stream_ptr(None, self._h.device)))
         out = desc.cpu().numpy() if isinstance(image, np.ndarray) else desc
         return out
 
@@ -256,8 +265,8 @@ class EfficientFeatures:
         """keypoints: 5 x N float32 CUDA tensor (GpuMat path: LOCATION and ANGLE rows only, size forced to 31,
         cuda_efficient_features.cu:250-263)."""
         torch = _torch()
-        _check_image_tensor(image)
-        if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda and keypoints.dtype == torch.float32
+        _check_image_tensor(image, self._h.device)
+        if not (isinstance(keypoints, torch.Tensor) and keypoints.is_cuda and keypoints.dtype == torch.float32 and keypoints.device == image.device
                 and keypoints.dim() == 2 and keypoints.shape[0] == ROWS_COUNT and keypoints.stride(1) == 1):
             raise EfError("keypoints must be a 5 x N float32 CUDA tensor")  # CV_Assert(tmp.rows == 5 && tmp.type() == CV_32F)
         n = keypoints.shape[1]
@@ -266,7 +275,7 @@ class EfficientFeatures:
             return desc
         self._h.check(self._h.L.ef_compute_rows_async(self._h.h, image.data_ptr(), image.stride(0), image.shape[1], image.shape[0],
                                                       keypoints.data_ptr(), keypoints.stride(0) * 4, n, desc.data_ptr(), desc.stride(0),
-                                                      _stream_ptr(stream)))
+                                                      _stream_ptr(stream, self._h.device)))
         return desc
 
     def detectAndComputeAsync(self, image, mask=None, useProvidedKeypoints=False, stream=None, want_descriptors=True):
@@ -284,7 +293,7 @@ class EfficientFeatures:
         torch = _torch()
         if useProvidedKeypoints:
             raise EfError("useProvidedKeypoints must be false")  # CV_Assert(!useProvidedKeypoints), :229
-        _check_image_tensor(image)  # CV_Assert(_image.type() == CV_8U), :228
+        _check_image_tensor(image, self._h.device)  # CV_Assert(_image.type() == CV_8U), :228
         nf = int(self._h.get(PARAM_MAX_FEATURES))
         kp = torch.empty((ROWS_COUNT, nf), dtype=torch.float32, device=image.device)
         desc = torch.empty((nf, self.descriptorSize()), dtype=torch.uint8, device=image.device) if want_descriptors else None
@@ -292,14 +301,15 @@ class EfficientFeatures:
         self._h.check(self._h.L.ef_detect_and_compute_async(
             self._h.h, image.data_ptr(), image.stride(0), image.shape[1], image.shape[0],
             kp.data_ptr(), kp.stride(0) * 4, desc.data_ptr() if desc is not None else None,
-            desc.stride(0) if desc is not None else 0, count.data_ptr(), _stream_ptr(stream)))
+            desc.stride(0) if desc is not None else 0, count.data_ptr(), _stream_ptr(stream, self._h.device)))
         return kp, desc, count
 
     def detectAndComputeBatchRaw(self, images, stream=None, want_descriptors=True, out=None):
         """New (not in the reference): F x H x W uint8 CUDA tensor -> (F x 5 x nfeatures, F x nfeatures x B, F counts)."""
         torch = _torch()
-        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8 and images.dim() == 3 and images.stride(2) == 1):
-            raise EfError("images must be an F x H x W uint8 CUDA tensor")
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8 and images.dim() == 3 and images.stride(2) == 1
+                and images.device == self._h.device):
+            raise EfError(f"images must be an F x H x W uint8 CUDA tensor on {self._h.device}")
         F, H, W = images.shape
         nf = int(self._h.get(PARAM_MAX_FEATURES))
         if out is None:
@@ -312,7 +322,7 @@ class EfficientFeatures:
             self._h.h, F, images.data_ptr(), images.stride(0), images.stride(1), W, H,
             kp.data_ptr(), kp.stride(0) * 4, kp.stride(1) * 4,
             desc.data_ptr() if desc is not None else None, desc.stride(0) if desc is not None else 0,
-            desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream)))
+            desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream, self._h.device)))
         return kp, desc, counts
 
     # ---- one oversized frame over several GPUs (ef_band_*; see efb200/tiling.py for the collective plumbing) ----
@@ -329,7 +339,7 @@ class EfficientFeatures:
         F, H, W = images.shape
         cand = torch.empty((F, self.bandCandidateBytes()), dtype=torch.uint8, device=images.device)
         self._h.check(self._h.L.ef_band_detect_async(self._h.h, shard, nshards, F, images.data_ptr(), images.stride(0), images.stride(1),
-                                                     W, H, cand.data_ptr(), _stream_ptr(stream)))
+                                                     W, H, cand.data_ptr(), _stream_ptr(stream, self._h.device)))
         self._band_images = images  # level 0 of the pyramid aliases the caller's image until bandFinish
         return cand
 
@@ -351,7 +361,7 @@ class EfficientFeatures:
         self._h.check(self._h.L.ef_band_finish_async(
             self._h.h, shard, nshards, F, all_cand.data_ptr(), kp.data_ptr(), kp.stride(0) * 4, kp.stride(1) * 4,
             desc.data_ptr() if desc is not None else None, desc.stride(0) if desc is not None else 0,
-            desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream)))
+            desc.stride(1) if desc is not None else 0, counts.data_ptr(), _stream_ptr(stream, self._h.device)))
         return kp, desc, counts
 
     def _host_call(self, images: np.ndarray, want_desc: bool):
@@ -366,7 +376,7 @@ class EfficientFeatures:
         counts = (C.c_int * F)()
         self._h.check(self._h.L.ef_detect_and_compute_host_batch(
             self._h.h, F, images.ctypes.data, images.strides[0], images.strides[1], W, H, kp.ctypes.data,
-            desc.ctypes.data if want_desc else None, counts, _stream_ptr(None)))
+            desc.ctypes.data if want_desc else None, counts, _stream_ptr(None, self._h.device)))
         kps = [kp[f][:, :counts[f]] for f in range(F)]
         descs = [desc[f][:counts[f]] if want_desc else None for f in range(F)]
         return kps, descs
@@ -377,7 +387,7 @@ class EfficientFeatures:
             if image.dtype != np.uint8 or image.ndim != 2:
                 raise EfError("image must be uint8 (CV_8UC1)")
             return torch.from_numpy(np.ascontiguousarray(image)).to(self._h.device)
-        _check_image_tensor(image)
+        _check_image_tensor(image, self._h.device)
         return image
 
     # ---- convert (cuda_efficient_features.cpp:323-349) --------------------------------------------
@@ -453,7 +463,7 @@ class EfficientFeatures:
         counts = (C.c_int * F)()
         self._h.check(self._h.L.ef_detect_and_compute_host_batch(
             self._h.h, F, ptr(frames), st[0], st[1], W, H, ptr(kp_out), ptr(desc_out) if desc_out is not None else None,
-            counts, _stream_ptr(stream)))
+            counts, _stream_ptr(stream, self._h.device)))
         return list(counts)
 
     def workspaceBytes(self) -> int:
@@ -485,7 +495,7 @@ class EfficientFeatures:
     def debugLevelCounts(self, frame: int = 0) -> np.ndarray:
         n = self.getNLevels()
         buf = (C.c_int * (3 * n))()
-        self._h.check(self._h.L.ef_debug_level_counts(self._h.h, frame, buf, _stream_ptr(None)))
+        self._h.check(self._h.L.ef_debug_level_counts(self._h.h, frame, buf, _stream_ptr(None, self._h.device)))
         return np.array(list(buf)).reshape(n, 3)
 
     def debugProject(self, sift128, path=0):
@@ -493,7 +503,7 @@ class EfficientFeatures:
         torch = _torch()
         assert sift128.is_cuda and sift128.dtype == torch.uint8 and sift128.dim() == 2 and sift128.shape[1] == 128 and sift128.is_contiguous()
         desc = torch.empty((sift128.shape[0], self.descriptorSize()), dtype=torch.uint8, device=sift128.device)
-        self._h.check(self._h.L.ef_debug_project_async(self._h.h, sift128.data_ptr(), sift128.shape[0], path, desc.data_ptr(), desc.stride(0), _stream_ptr(None)))
+        self._h.check(self._h.L.ef_debug_project_async(self._h.h, sift128.data_ptr(), sift128.shape[0], path, desc.data_ptr(), desc.stride(0), _stream_ptr(None, self._h.device)))
         return desc
 
     def debugKeepProjection(self, keep=True):
@@ -563,8 +573,9 @@ class _Describer:
     SIZE_512_BITS, SIZE_256_BITS = 100, 101
 
     def __init__(self, dtype, scale, max_width, max_height, max_keypoints, device):
+        # compute-only handle: tables and per-keypoint scratch, no detection workspace (the reference describers hold only their tables)
         self._ef = EfficientFeatures(nfeatures=1, dtype=dtype, max_width=max_width, max_height=max_height,
-                                     max_keypoints=max_keypoints, device=device)
+                                     max_keypoints=max_keypoints, device=device, flags=FLAG_COMPUTE_ONLY)
         self._ef._h.set(PARAM_DESC_SCALE, scale)
 
     def compute(self, image, keypoints):

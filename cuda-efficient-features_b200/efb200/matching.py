@@ -51,18 +51,26 @@ class BFMatcher:
         if normType != NORM_HAMMING:
             raise EfError("only NORM_HAMMING (defaultNorm() of the path's descriptors) is implemented")
         self.crossCheck = bool(crossCheck)
-        self._scratch = None
+        self._scratch = {}      # one scratch buffer per (device, stream): concurrent streams never share one
 
     @staticmethod
     def create(normType=NORM_HAMMING, crossCheck=False) -> "BFMatcher":
         return BFMatcher(normType, crossCheck)
 
-    def _scratch_for(self, nq, nt, device):
+    def _scratch_for(self, nq, nt, device, stream):
+        """Scratch of the call, owned per (device, stream).  The kernels run on `stream`, which need not be torch's current stream:
+        every tensor they touch is handed to the caching allocator with record_stream(), so that memory freed while the kernels are
+        still in flight (a replaced scratch, the results, temporaries made from host descriptors) is not recycled under them."""
         torch = _torch()
         need = int(_lib().ef_match_scratch_bytes(nq, nt))
-        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
-            self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._scratch
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        key = (device, int(st.cuda_stream))
+        sc = self._scratch.get(key)
+        if sc is None or sc.numel() < need:
+            sc = torch.empty(need, dtype=torch.uint8, device=device)
+            self._scratch[key] = sc
+        sc.record_stream(st)
+        return sc, st
 
     # ---- device forms: int32 CUDA tensors, no host synchronisation ----
     def knnMatchAsync(self, query, train, k=2, stream=None):
@@ -73,9 +81,14 @@ class BFMatcher:
         nq, nt = q.shape[0], t.shape[0]
         idx = torch.empty((nq, k), dtype=torch.int32, device=q.device)
         dist = torch.empty((nq, k), dtype=torch.int32, device=q.device)
-        sc = self._scratch_for(nq, nt, q.device)
+        if t.device != q.device:
+            from . import EfError
+            raise EfError("query and train descriptors must live on the same device")
+        sc, st = self._scratch_for(nq, nt, q.device, stream)
+        for a in (q, t, idx, dist):
+            a.record_stream(st)
         _check(_lib().ef_match_knn_async(q.data_ptr(), q.stride(0) if nq else 0, nq, t.data_ptr(), t.stride(0) if nt else 0, nt, q.shape[1], k,
-                                         idx.data_ptr(), dist.data_ptr(), sc.data_ptr(), _stream_ptr(stream)))
+                                         idx.data_ptr(), dist.data_ptr(), sc.data_ptr(), _stream_ptr(st, q.device)))
         return idx, dist
 
     def matchAsync(self, query, train, stream=None):
@@ -89,9 +102,14 @@ class BFMatcher:
             return idx[:, 0], dist[:, 0]
         idx = torch.empty(nq, dtype=torch.int32, device=q.device)
         dist = torch.empty(nq, dtype=torch.int32, device=q.device)
-        sc = self._scratch_for(nq, nt, q.device)
+        if t.device != q.device:
+            from . import EfError
+            raise EfError("query and train descriptors must live on the same device")
+        sc, st = self._scratch_for(nq, nt, q.device, stream)
+        for a in (q, t, idx, dist):
+            a.record_stream(st)
         _check(_lib().ef_match_cross_check_async(q.data_ptr(), q.stride(0) if nq else 0, nq, t.data_ptr(), t.stride(0) if nt else 0, nt, q.shape[1],
-                                                 idx.data_ptr(), dist.data_ptr(), sc.data_ptr(), _stream_ptr(stream)))
+                                                 idx.data_ptr(), dist.data_ptr(), sc.data_ptr(), _stream_ptr(st, q.device)))
         return idx, dist
 
     # ---- OpenCV-shaped forms: DMatch records on the host ----
@@ -126,8 +144,11 @@ def ratio_cross_filter(idx12, dist12, idx21, dist21, uniqueness=0.9, stream=None
     for a in (idx12, dist12, idx21, dist21):
         assert a.is_cuda and a.dtype == torch.int32 and a.is_contiguous() and a.dim() == 2 and a.shape[1] == 2
     out = torch.empty(nq, dtype=torch.int32, device=idx12.device)
+    st = stream if stream is not None else torch.cuda.current_stream(idx12.device)
+    for a in (idx12, dist12, idx21, dist21, out):
+        a.record_stream(st)
     _check(_lib().ef_match_ratio_cross_async(idx12.data_ptr(), dist12.data_ptr(), nq, idx21.data_ptr(), dist21.data_ptr(), nt,
-                                             float(uniqueness), out.data_ptr(), _stream_ptr(stream)))
+                                             float(uniqueness), out.data_ptr(), _stream_ptr(st, idx12.device)))
     return out
 
 
@@ -144,7 +165,9 @@ def cvtColorToGray(image, stream=None):
         raise EfError("Image should be 8UC1, 8UC3 or 8UC4")  # CV_Error(StsBadArg, ...), sample_common.cpp:44
     H, W, cn = image.shape
     gray = torch.empty((H, W), dtype=torch.uint8, device=image.device)
-    rc = _lib().ef_bgr_to_gray_async(image.data_ptr(), image.stride(0), W, H, cn, gray.data_ptr(), gray.stride(0), _stream_ptr(stream))
+    st = stream if stream is not None else torch.cuda.current_stream(image.device)
+    image.record_stream(st); gray.record_stream(st)
+    rc = _lib().ef_bgr_to_gray_async(image.data_ptr(), image.stride(0), W, H, cn, gray.data_ptr(), gray.stride(0), _stream_ptr(st, image.device))
     if rc != 0:
         raise EfError(f"ef_bgr_to_gray_async failed with status {rc}")
     return gray

@@ -62,7 +62,13 @@ typedef struct ef_params {
     int max_batch;        /* frames per batched call */
     int max_keypoints;    /* capacity of the compute-only API (>= nfeatures) */
     int device;           /* CUDA device ordinal */
+    int flags;            /* EF_FLAG_*; 0 = full detectAndCompute handle */
 } ef_params;
+
+/* ef_params.flags.  EF_FLAG_COMPUTE_ONLY: the handle serves ef_compute_async / ef_compute_rows_async only (cv::cuda::BAD,
+ * cv::cuda::HashSIFT: the reference describers hold nothing but their tables, src/cuda_bad.cpp:36-44): no detection
+ * workspace and no host-API staging are allocated; the detect entry points return EF_ERR_UNSUPPORTED. */
+enum { EF_FLAG_COMPUTE_ONLY = 1 };
 
 typedef struct ef_handle ef_handle;
 

@@ -4,12 +4,26 @@
 // into oracle/_ref/libef_ref.so, which pins oracle/ef_oracle.c.  Only the members those two files
 // touch are provided.  Third-party arithmetic defined here: cv::integral (exact,
 // wrapping int32), cv::gemm (fp32 out, double accumulation, ascending k), cvRound (half-even).
+//
+// Round 2: the same stand-in also carries what the reference's PUBLIC headers, its own test
+// (tests/descriptor_test.cpp) and its benchmark sample (samples/sample_benchmark.cpp, sample_common.cpp) need, so that they
+// compile UNMODIFIED against cuda-efficient-features_b200/cpp/opencv_adapter.cpp + libef_b200.so (oracle/Makefile, target
+// `adapter`): cv::Exception, Vec / Scalar / DMatch, Mat ROI / clone / copyTo, _InputArray kinds (MAT, CUDA_GPU_MAT),
+// absdiff / countNonZero, format, CommandLineParser; cv::cuda::GpuMat / Stream live in core/cuda.hpp (pulled in only when
+// the CUDA runtime headers are on the include path).  None of this is product code.
 #pragma once
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <iostream>
+#include <map>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -30,9 +44,21 @@
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC4 CV_MAKETYPE(CV_32F, 4)
 
-#define CV_Error(code, msg) throw std::runtime_error(std::string(msg))
-#define CV_Assert(expr) do { if (!(expr)) throw std::runtime_error("CV_Assert failed: " #expr); } while (0)
+namespace cv
+{
+// cv::Exception: what CV_Error / CV_Assert throw
+class Exception : public std::runtime_error
+{
+public:
+    Exception(int c, const std::string& m) : std::runtime_error(m), code(c), msg(m) {}
+    int code; std::string msg;
+};
+}
+#define CV_Error(code_, msg_) throw cv::Exception((int)(code_), std::string(msg_))
+#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception(-215, "CV_Assert failed: " #expr); } while (0)
 #define CV_DbgAssert(expr) ((void)0)
 
 typedef unsigned char uchar;
@@ -45,14 +71,33 @@ static inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
 namespace cv
 {
 using ::uchar;
-namespace Error { enum { StsBadArg = -5 }; }
+namespace Error { enum Code { StsBadArg = -5, StsAssert = -215, GpuApiCallError = -217 }; }
 enum { NORM_HAMMING = 6 };
+typedef std::string String;
 enum { GEMM_1_T = 1, GEMM_2_T = 2, GEMM_3_T = 4 };
 
 template <typename T> using Ptr = std::shared_ptr<T>;
 template <typename T, typename... A> Ptr<T> makePtr(A&&... a) { return std::make_shared<T>(std::forward<A>(a)...); }
 
-template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T a, T b) : x(a), y(b) {} };
+template <typename T> struct Point_
+{
+    T x, y; Point_() : x(0), y(0) {} Point_(T a, T b) : x(a), y(b) {}
+    Point_& operator*=(T s) { x *= s; y *= s; return *this; }
+};
+template <typename T, int N> struct Vec
+{
+    T val[N];
+    Vec() { for (T& v : val) v = T(); }
+    Vec(T a, T b) { static_assert(N == 2, ""); val[0] = a; val[1] = b; }
+    Vec(T a, T b, T c, T d) { static_assert(N == 4, ""); val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+    T& operator[](int i) { return val[i]; }
+    const T& operator[](int i) const { return val[i]; }
+};
+typedef Vec<short, 2> Vec2s;
+typedef Vec<float, 4> Vec4f;
+struct Scalar { double val[4]; static Scalar all(double v) { Scalar s; for (double& x : s.val) x = v; return s; } };
+struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = FLT_MAX; };
+struct Range { int start, end; Range(int s, int e) : start(s), end(e) {} };
 typedef Point_<float> Point2f;
 template <typename T> struct Size_
 {
@@ -63,6 +108,7 @@ template <typename T> struct Size_
 };
 typedef Size_<int> Size;
 typedef Size_<float> Size2f;
+static inline std::ostream& operator<<(std::ostream& os, const Size& s) { return os << "[" << s.width << " x " << s.height << "]"; }
 
 struct KeyPoint
 {
@@ -70,6 +116,8 @@ struct KeyPoint
     KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
     KeyPoint(float x, float y, float s, float a = -1, float r = 0, int o = 0, int c = -1)
         : pt(x, y), size(s), angle(a), response(r), octave(o), class_id(c) {}
+    KeyPoint(Point2f p, float s, float a = -1, float r = 0, int o = 0, int c = -1)
+        : pt(p), size(s), angle(a), response(r), octave(o), class_id(c) {}
 };
 
 struct Matx23f
@@ -136,6 +184,20 @@ public:
     template <typename T> T& at(int i, int j) { return ((T*)(data + (size_t)i * step.p[0]))[j]; }
     template <typename T> const T& at(int i, int j) const { return ((const T*)(data + (size_t)i * step.p[0]))[j]; }
 
+    // single-index element access of an n x 1 matrix (tmp.at<Vec4f>(i)); ROI headers share the storage
+    template <typename T> T& at(int i) { return *(T*)(data + (size_t)i * step.p[0]); }
+    template <typename T> const T& at(int i) const { return *(const T*)(data + (size_t)i * step.p[0]); }
+    bool isContinuous() const { return dims != 2 || step.p[0] == (size_t)cols * elemSize(); }
+    Mat colRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * elemSize(); m.cols = b - a; m.size_[1] = b - a; return m; }
+    Mat rowRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * step.p[0]; m.rows = b - a; m.size_[0] = b - a; return m; }
+    void copyTo(Mat& dst) const
+    {
+        CV_Assert(dims == 2);
+        dst.create(rows, cols, type_);
+        for (int i = 0; i < rows; i++) std::memcpy(dst.ptr<uchar>(i), ptr<uchar>(i), (size_t)cols * elemSize());
+    }
+    Mat clone() const { Mat m; copyTo(m); return m; }
+
     Mat& operator=(double v)
     {   // `hist = 0` in hash_sift.cpp:229 (only zero is needed, any depth)
         CV_Assert(v == 0 && store_); std::memset(data, 0, total_); return *this;
@@ -152,25 +214,42 @@ private:
     std::shared_ptr<uchar> store_;
 };
 
+namespace cuda { class GpuMat; }
+
+// InputArray / OutputArray proxies: a Mat, a cuda::GpuMat or nothing (noArray()); kind() like OpenCV's _InputArray::KindFlag
 class _InputArray
 {
 public:
-    _InputArray() : m_(nullptr) {}
-    _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
+    enum KindFlag { NONE = 0, MAT = 1 << 16, CUDA_GPU_MAT = 9 << 16 };
+    _InputArray() : kind_(NONE), m_(nullptr), g_(nullptr) {}
+    _InputArray(const Mat& m) : kind_(MAT), m_(const_cast<Mat*>(&m)), g_(nullptr) {}
+    _InputArray(const cuda::GpuMat& g) : kind_(CUDA_GPU_MAT), m_(nullptr), g_(const_cast<cuda::GpuMat*>(&g)) {}
+    KindFlag kind() const { return kind_; }
     Mat getMat() const { return m_ ? *m_ : Mat(); }
+    // the members below also serve the GpuMat kind; they are defined in core/cuda.hpp when the CUDA headers are present
+    inline cuda::GpuMat getGpuMat() const;
+    inline int type() const;
+    inline bool empty() const;
+    inline Size size() const;
 protected:
-    Mat* m_;
+    KindFlag kind_; Mat* m_; cuda::GpuMat* g_;
 };
 class _OutputArray : public _InputArray
 {
 public:
     _OutputArray() {}
     _OutputArray(Mat& m) : _InputArray(m) {}
-    void create(int r, int c, int t) const { m_->create(r, c, t); }
-    void release() const { if (m_) m_->release(); }
+    _OutputArray(cuda::GpuMat& g) : _InputArray(g) {}
+    bool needed() const { return kind_ != NONE; }
+    inline void create(int r, int c, int t) const;
+    inline void create(Size s, int t) const { create(s.height, s.width, t); }
+    inline void release() const;
+    Mat& getMatRef() const { return *m_; }
+    cuda::GpuMat& getGpuMatRef() const { return *g_; }
 };
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
+static inline const _OutputArray& noArray() { static const _OutputArray none; return none; }
 
 // cv::integral for CV_8UC1 -> CV_32SC1, (h+1)x(w+1), exact with int32 wrap-around (bad.cpp:286)
 static inline void integral(const Mat& src, Mat& sum)
@@ -204,5 +283,115 @@ static inline void gemm(const Mat& A, const Mat& B, double alpha, const Mat&, do
             c[j] = (float)acc;
         }
     }
+}
+} // namespace cv
+
+#if __has_include(<cuda_runtime.h>)
+#include "core/cuda.hpp"
+#else
+// host-only build (oracle/_ref/libef_ref.so): the proxies only ever hold a Mat
+namespace cv
+{
+inline int _InputArray::type() const { return m_ ? m_->type() : 0; }
+inline bool _InputArray::empty() const { return !m_ || m_->empty(); }
+inline Size _InputArray::size() const { return m_ ? m_->size() : Size(); }
+inline void _OutputArray::create(int r, int c, int t) const { CV_Assert(m_); m_->create(r, c, t); }
+inline void _OutputArray::release() const { if (m_) m_->release(); }
+}
+#endif
+
+namespace cv
+{
+// cv::absdiff / cv::countNonZero for single-channel 8-bit matrices (tests/descriptor_test.cpp:40-42)
+static inline void absdiff(const Mat& a, const Mat& b, Mat& dst)
+{
+    CV_Assert(a.type() == CV_8UC1 && b.type() == CV_8UC1 && a.rows == b.rows && a.cols == b.cols);
+    dst.create(a.rows, a.cols, CV_8UC1);
+    for (int i = 0; i < a.rows; i++) {
+        const uchar* pa = a.ptr<uchar>(i); const uchar* pb = b.ptr<uchar>(i); uchar* pd = dst.ptr<uchar>(i);
+        for (int j = 0; j < a.cols; j++) pd[j] = (uchar)(pa[j] > pb[j] ? pa[j] - pb[j] : pb[j] - pa[j]);
+    }
+}
+static inline int countNonZero(const Mat& a)
+{
+    CV_Assert(a.type() == CV_8UC1);
+    int n = 0;
+    for (int i = 0; i < a.rows; i++) { const uchar* p = a.ptr<uchar>(i); for (int j = 0; j < a.cols; j++) n += p[j] != 0; }
+    return n;
+}
+static inline String format(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); std::vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    return String(buf);
+}
+
+// cv::CommandLineParser for key strings of the form "{ name alias | default | help }" (samples/sample_benchmark.cpp:27-37)
+class CommandLineParser
+{
+public:
+    CommandLineParser(int argc, const char* const argv[], const String& keys)
+    {
+        size_t pos = 0;
+        while ((pos = keys.find('{', pos)) != String::npos) {
+            const size_t end = keys.find('}', pos);
+            std::vector<String> f = split(keys.substr(pos + 1, end - pos - 1), '|');
+            f.resize(3);
+            Key k; k.def = trim(f[1]); k.help = trim(f[2]); k.value = k.def == "<none>" ? "" : k.def; k.set = false;
+            std::istringstream names(f[0]); String nm;
+            while (names >> nm) k.names.push_back(nm);
+            if (!k.names.empty()) { if (k.names[0][0] == '@') positional_.push_back((int)keys_.size()); keys_.push_back(k); }
+            pos = end;
+        }
+        size_t npos = 0;
+        for (int i = 1; i < argc; i++) {
+            String a = argv[i];
+            if (a.rfind("--", 0) == 0 || (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1]))) {
+                a = a.substr(a.find_first_not_of('-'));
+                String v = "true"; const size_t eq = a.find('=');
+                if (eq != String::npos) { v = a.substr(eq + 1); a = a.substr(0, eq); }
+                Key* k = find(a);
+                if (k) { k->value = v; k->set = true; } else errors_.push_back("unknown option: " + a);
+            } else if (npos < positional_.size()) { Key& k = keys_[positional_[npos++]]; k.value = a; k.set = true; }
+        }
+    }
+    bool has(const String& name) const { const Key* k = const_cast<CommandLineParser*>(this)->find(name); return k && (k->set || (!k->def.empty() && k->def != "<none>")); }
+    template <typename T> T get(const String& name) const
+    {
+        const Key* k = const_cast<CommandLineParser*>(this)->find(name);
+        T out = T();
+        if (!k) { errors_.push_back("undeclared key: " + name); return out; }
+        if (k->value.empty()) { errors_.push_back("missing parameter: " + name); return out; }
+        std::istringstream is(k->value);
+        if (!(is >> out)) errors_.push_back("cannot parse parameter: " + name);
+        return out;
+    }
+    bool check() const { return errors_.empty(); }
+    void printErrors() const { for (const String& e : errors_) std::cout << "ERROR: " << e << std::endl; }
+    void printMessage() const
+    {
+        std::cout << "Usage: [params]";
+        for (int i : positional_) std::cout << " " << keys_[i].names[0].substr(1);
+        std::cout << std::endl;
+        for (const Key& k : keys_) {
+            std::cout << "\t";
+            for (size_t i = 0; i < k.names.size(); i++) std::cout << (i ? ", " : "") << (k.names[i][0] == '@' ? "" : "--") << k.names[i];
+            if (!k.def.empty()) std::cout << " (value:" << k.def << ")";
+            std::cout << "\n\t\t" << k.help << std::endl;
+        }
+    }
+private:
+    struct Key { std::vector<String> names; String def, help, value; bool set; };
+    static String trim(const String& s) { const size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t"); return a == String::npos ? "" : s.substr(a, b - a + 1); }
+    static std::vector<String> split(const String& s, char c) { std::vector<String> v; std::istringstream is(s); String t; while (std::getline(is, t, c)) v.push_back(t); return v; }
+    Key* find(const String& name) { for (Key& k : keys_) for (const String& n : k.names) if (n == name) return &k; return nullptr; }
+    std::vector<Key> keys_; std::vector<int> positional_; mutable std::vector<String> errors_;
+};
+template <> inline String CommandLineParser::get<String>(const String& name) const
+{
+    const Key* k = const_cast<CommandLineParser*>(this)->find(name);
+    if (!k) { errors_.push_back("undeclared key: " + name); return ""; }
+    if (k->value.empty()) errors_.push_back("missing parameter: " + name);
+    return k->value;
 }
 } // namespace cv

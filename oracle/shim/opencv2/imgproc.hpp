@@ -9,4 +9,5 @@ enum { INTER_CUBIC = 2, WARP_INVERSE_MAP = 16, BORDER_REPLICATE = 1 };
 static inline void cvtColor(const Mat&, Mat&, int) { CV_Error(Error::StsBadArg, "shim: colour input not supported"); }
 static inline void warpAffine(const Mat&, Mat&, const Matx23f&, Size, int, int) { CV_Error(Error::StsBadArg, "shim: warpAffine not provided"); }
 static inline void GaussianBlur(const Mat&, Mat&, Size, double, double) { CV_Error(Error::StsBadArg, "shim: GaussianBlur not provided"); }
+static inline void resize(const Mat&, Mat&, Size) { CV_Error(Error::StsBadArg, "shim: resize not provided"); }
 } // namespace cv
