@@ -108,7 +108,7 @@ public:
             const KeyPoint& k = keypoints[i];
             hkpts_[4 * i] = k.pt.x; hkpts_[4 * i + 1] = k.pt.y; hkpts_[4 * i + 2] = k.size; hkpts_[4 * i + 3] = k.angle;
         }
-        const Mat hk(n, 1, CV_32FC4, hkpts_.data());
+        const Mat hk(1, n, CV_32FC4, hkpts_.data());   // ONE row: contiguous on the device whatever pitch the allocator gives multi-row matrices
         dkpts_.upload(hk, stream);
         run(img, n, descriptors, stream, [&](GpuMat& out) {
             return ef_compute_async(hd_.h, img.data, img.step, img.cols, img.rows, dkpts_.ptr<float>(), n, out.data, out.step, StreamAccessor::getStream(stream));

@@ -61,7 +61,8 @@ public:
         if (r <= 0 || c <= 0) { flags = t; return; }
         flags = t; rows = r; cols = c; own_rows_ = r; own_cols_ = c;
         void* p = nullptr; size_t pitch = 0;
-        EF_SHIM_CUDA(cudaMallocPitch(&p, &pitch, (size_t)c * elemSize(), (size_t)r));
+        if (r > 1 && c > 1) EF_SHIM_CUDA(cudaMallocPitch(&p, &pitch, (size_t)c * elemSize(), (size_t)r));
+        else { pitch = (size_t)c * elemSize(); EF_SHIM_CUDA(cudaMalloc(&p, pitch * (size_t)r)); }   // OpenCV: a single row or column is continuous
         store_.reset((uchar*)p, [](uchar* q) { cudaFree(q); });
         data = (uchar*)p; step = pitch;
     }
