@@ -7,7 +7,11 @@
 A step = one detectAndCompute pass over one batch of `--batch` synthetic 4K frames per GPU (HashSIFT-512,
 nfeatures 40000 by default = BASELINE.json configs[3]/[4] workload at the 4K resolution the metric is quoted on).
 Frames are sharded over ranks (one process per GPU, no data-path collective): scaling = weak.
-Prints ONE JSON line (rank 0).
+Both arms read the SAME pixels: frame f of the workload is pix(f, y, x) = lowbias32(seed ^ ((f * H + y) * W + x)) >> 24 with
+seed 0xEFB20004, generated on the device for the product arm (ef_synth_frames_async) and by the oracle for the CPU arm.
+The line also carries one driver-run number for every other BASELINE.json config under "configs" (detect-only 4K, compute-only on
+40 000 keypoints, 8K detectAndCompute, BAD-512 on 64 frames split over the ranks = strong scaling, and -- at N > 1 -- two 8K
+frames cut into bands over the ranks).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -22,6 +26,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "cuda-efficient-features_b200"))
+SEED = 0xEFB20004            # seed = 0xEFB20000 + config id; one seed for every bench workload, frames are numbered globally
 
 DESC = {"BAD_256": (0, 32), "BAD_512": (1, 64), "HASH_SIFT_256": (2, 32), "HASH_SIFT_512": (3, 64)}
 
@@ -85,6 +90,65 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def kernel_source_sha():
+    """sha256 over the kernel sources: profiles/traffic.json records it, so a capture taken from other kernels is never reported"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "cuda-efficient-features_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def pin_host_to_gpu(local_rank, local_world):
+    """Pin this rank's host threads (and, by first touch + preferred-node policy, its pinned staging buffers) to the CPUs of the
+    GPU's NUMA node, sharing the node's CPUs evenly between the ranks that sit on it.  Returns what was done (for the JSON line)."""
+    info = {"numa_node": None, "cpus": None, "pinned": False}
+    try:
+        import torch
+        def node_of(i):
+            pr = torch.cuda.get_device_properties(i)
+            path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+            try:
+                return int(open(path).read().strip())
+            except Exception:
+                return -1
+        def parse(cl):
+            out = []
+            for part in cl.strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-"); out += list(range(int(a), int(b) + 1))
+                elif part:
+                    out.append(int(part))
+            return out
+        nodes = [node_of(i) for i in range(local_world)]
+        node = nodes[local_rank]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = allowed
+        if node >= 0:
+            try:
+                on_node = set(parse(open(f"/sys/devices/system/node/node{node}/cpulist").read()))
+                cpus = [c for c in allowed if c in on_node] or allowed
+            except Exception:
+                pass
+        peers = [r for r in range(local_world) if nodes[r] == node]
+        k, m = peers.index(local_rank), len(peers)
+        per = max(1, len(cpus) // m)
+        mine = cpus[k * per:(k + 1) * per] if (k + 1) * per <= len(cpus) else cpus[-per:]
+        os.sched_setaffinity(0, set(mine))
+        if node >= 0:
+            try:    # set_mempolicy(MPOL_PREFERRED, node): host staging buffers land on the GPU's node
+                import ctypes
+                libc = ctypes.CDLL(None, use_errno=True)
+                mask = ctypes.c_ulong(1 << node)
+                libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            except Exception:
+                pass
+        info = {"numa_node": node, "cpus": f"{mine[0]}-{mine[-1]}" if mine else None, "ncpus": len(mine), "pinned": True}
+    except Exception as e:  # never fatal: affinity is an optimisation
+        info["error"] = str(e)[:80]
+    return info
+
+
 def cpu_reference_run(args, steps, warmup, frames_per_step=1, threads=None):
     """Times the CPU path (oracle = the reference's CPU descriptors + CPU restatement of its CUDA-only detector)."""
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -92,7 +156,7 @@ def cpu_reference_run(args, steps, warmup, frames_per_step=1, threads=None):
     o = efo.Oracle()
     threads = threads or o.max_threads()
     o.set_threads(threads)
-    frames = [o.synth_frame(0xEFB20004, f, args.width, args.height) for f in range(frames_per_step)]
+    frames = [o.synth_frame(SEED, f, args.width, args.height) for f in range(frames_per_step)]   # frame 0.. of the product arm's rank 0
     params = o.make_params(nfeatures=args.nfeatures, desc_type=DESC[args.desc][0])
     nk = 0
     for _ in range(warmup):
@@ -121,6 +185,7 @@ def main():
     ap.add_argument("--desc", default="HASH_SIFT_512", choices=list(DESC))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-config numbers under \"configs\"")
     ap.add_argument("--tiled", action="store_true",
                     help="instead of sharding frames, cut EVERY frame into horizontal bands over the ranks (ef_band_*): image broadcast from "
                          "rank 0, all-gather of the band candidates and MAX all-reduce of the descriptors inside the timed region; strong scaling")
@@ -164,9 +229,11 @@ def main():
     B, H, W = args.batch, args.height, args.width
     dtype_id, dbytes = DESC[args.desc]
 
-    gen = torch.Generator(device="cpu").manual_seed(0xEFB2 + rank)
-    frames_host = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
-    frames = frames_host.to(dev)
+    host = pin_host_to_gpu(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    # the pinned counter-based generator, on the device; rank r owns frames [r B, (r + 1) B) of the global sequence (tiled: all ranks the same)
+    frames = efb200.synth_frames(B, H, W, SEED, first_frame=0 if args.tiled else rank * B, device=dev)
+    frames_host = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    frames_host.copy_(frames)
     ef = efb200.EfficientFeatures.create(nfeatures=args.nfeatures, dtype=dtype_id, max_width=W, max_height=H, max_batch=B, device=local_rank)
     kp = torch.empty((B, 5, args.nfeatures), dtype=torch.float32, device=dev)
     desc = torch.empty((B, args.nfeatures, dbytes), dtype=torch.uint8, device=dev)
@@ -243,6 +310,77 @@ def main():
 
     clocks = sampler.finish() if sampler else None   # sampled through both timed regions (device-resident and host-buffer)
 
+    # ---- one driver-run number for every other BASELINE.json config (all ranks take part: the barriers and max-over-ranks apply)
+    def timed(fn, steps, warmup=2):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t_ms = a.elapsed_time(b)
+        if world > 1:
+            tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt[0].item())
+        return t_ms / steps
+
+    extras = {}
+    if not args.no_extras and not args.tiled and (W, H) == (3840, 2160):
+        from efb200.sharding import shard_range
+        # configs[1]: detect-only (FAST pyramid + radius-15 NMS + top-K + angles), same frames
+        t1 = timed(lambda: ef.detectAndComputeBatchRaw(frames, want_descriptors=False, out=(kp, None, counts)), 5)
+        extras["configs[1] detect-only 4K nfeatures 40000 r 15"] = {
+            "ms_per_step": t1, "frames_per_step": world * B, "Mpix_per_s": world * B * W * H / (t1 * 1e-3) / 1e6, "frames_per_s": world * B / (t1 * 1e-3), "scaling": "weak"}
+        # configs[2]: compute-only on 40 000 precomputed keypoints (detector with r = 7 fills every quota at 4K), through the 5 x N
+        # GpuMat path = benchmark-type 2 of samples/sample_benchmark.cpp:129-139; each rank describes its own frame
+        ef2 = efb200.EfficientFeatures.create(nfeatures=40000, nonmaxRadius=7, dtype=efb200.BAD_512, max_width=W, max_height=H, max_keypoints=40000, device=local_rank)
+        k5 = ef2.detectAsync(frames[0]).contiguous()
+        c2 = {"keypoints": int(k5.shape[1])}
+        for name, dt_id in (("BAD_512", efb200.BAD_512), ("HASH_SIFT_512", efb200.HASH_SIFT_512)):
+            ef2.setDescriptorType(dt_id)
+            t2 = timed(lambda: ef2.computeAsync(frames[0], k5), 20)
+            c2[name] = {"ms_per_call": t2, "Mkeypoints_per_s": world * int(k5.shape[1]) / (t2 * 1e-3) / 1e6}
+        extras["configs[2] compute-only 40000 keypoints 4K"] = c2
+        del ef2
+        # configs[3]: 7680x4320 HashSIFT-512 (every quota binds: 40 000 delivered keypoints per frame)
+        B8 = 4
+        ef8 = efb200.EfficientFeatures.create(nfeatures=40000, dtype=efb200.HASH_SIFT_512, max_width=7680, max_height=4320, max_batch=B8, device=local_rank)
+        frames8 = efb200.synth_frames(B8, 4320, 7680, SEED, first_frame=100000 + rank * B8, device=dev)
+        out8 = (kp[:B8], desc[:B8], counts[:B8])
+        t3 = timed(lambda: ef8.detectAndComputeBatchRaw(frames8, out=out8), 5)
+        extras["configs[3] detectAndCompute HASH_SIFT_512 8K"] = {
+            "ms_per_step": t3, "frames_per_step": world * B8, "Mpix_per_s": world * B8 * 7680 * 4320 / (t3 * 1e-3) / 1e6,
+            "frames_per_s": world * B8 / (t3 * 1e-3), "keypoints_per_frame": float(counts[:B8].float().mean().item()), "scaling": "weak"}
+        # N > 1: the same two 8K frames cut into horizontal bands over the ranks (ef_band_*): strong scaling of ONE oversized frame
+        if world > 1:
+            from efb200 import tiling
+            fr2 = efb200.synth_frames(2, 4320, 7680, SEED, first_frame=100000, device=dev)
+            out2 = (kp[:2], desc[:2], counts[:2])
+            t5 = timed(lambda: tiling.detect_and_compute_tiled(ef8, fr2, src=0, out=out2), 5)
+            extras["oversized frame: 2 x 8K HASH_SIFT_512 cut into bands"] = {
+                "ms_per_step": t5, "frames_per_step": 2, "Mpix_per_s": 2 * 7680 * 4320 / (t5 * 1e-3) / 1e6, "bands": world, "scaling": "strong",
+                "collectives": tiling.COLLECTIVES}
+            del fr2
+        del ef8, frames8
+        # configs[4]: BAD-512, ONE batch of 64 4K frames split over the ranks (strong scaling), sub-batches of <= B frames per call
+        a64, b64 = shard_range(64, rank, world)
+        n64 = b64 - a64
+        f64 = efb200.synth_frames(n64, H, W, SEED, first_frame=200000 + a64, device=dev) if n64 else None
+        ef.setDescriptorType(efb200.BAD_512)
+        def run64():
+            for o in range(0, n64, B):
+                n = min(B, n64 - o)
+                ef.detectAndComputeBatchRaw(f64[o:o + n], out=(kp[:n], desc[:n], counts[:n]))
+        t4 = timed(run64, 3)
+        ef.setDescriptorType(dtype_id)
+        extras["configs[4] BAD_512 batch of 64 4K frames split over the ranks"] = {
+            "ms_per_batch": t4, "frames": 64, "frames_per_rank": n64, "Mpix_per_s": 64 * W * H / (t4 * 1e-3) / 1e6, "frames_per_s": 64 / (t4 * 1e-3), "scaling": "strong"}
+        del f64
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -265,11 +403,18 @@ def main():
     # written by tools/ncu_summary.py for a batch of `frames` frames), rescaled to this run's batch
     traffic_file = ROOT / "profiles" / "traffic.json"
     tr = {}
+    traffic_note = "no capture"
     if traffic_file.exists():
         try:
             tr = json.loads(traffic_file.read_text())
         except Exception:
             tr = {}
+        # a capture is only reported for the kernels it was taken from (tools/ncu_summary.py records the hash of csrc/)
+        if tr.get("_src_sha") != kernel_source_sha():
+            traffic_note = f"capture {tr.get('_src_sha')} is stale for kernels {kernel_source_sha()}: traffic not reported"
+            tr = {}
+        else:
+            traffic_note = tr.get("_note", "")
     def with_traffic(r):
         v = tr.get(("describe_bad" if (r["kernel"] == "describe" and dtype_id < 2) else r["kernel"]))
         if isinstance(v, (int, float)) and tr.get("_frames"):
@@ -306,7 +451,8 @@ def main():
             "keypoints_per_frame": n_frame, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_pyramid": roofline_pyr, "stage_ms_per_step": per_call,
             "stage_roofline_frac": {k: round(v["frac"], 5) for k, v in rooflines.items()},
-            "stage_issue_frac": stage_issue, "stage_smem_pipe_frac": stage_smem, "cpu_baseline": cpu_baseline}
+            "stage_issue_frac": stage_issue, "stage_smem_pipe_frac": stage_smem, "traffic_source": traffic_note,
+            "host": host, "configs": extras, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -49,3 +49,35 @@ extern "C" int ef_bgr_to_gray_async(const uint8_t* d_src, size_t src_pitch, int 
     EF_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? EF_OK : EF_ERR_CUDA;
 }
+
+// ---- synthetic frames (measurement support; SURVEY 8d "pinned counter-based generator"): pix(f, y, x) = lowbias32(seed ^ ((f * H + y) * W + x)) >> 24,
+// the generator of the CPU arm (oracle efo_synth_frame) restated on the device so that bench.py feeds BOTH arms the same pixels
+// without an upload.  One thread = 4 adjacent pixels, one 32-bit store when aligned.
+__device__ __forceinline__ unsigned ef_lowbias32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(256) ef_synth_frames_kernel(uint8_t* __restrict__ dst, size_t pitch, size_t stride, int w, int h, unsigned seed, unsigned first_frame)
+{
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y;
+    if (x0 >= w) return;
+    const unsigned frame = first_frame + blockIdx.z;
+    const unsigned base = (frame * (unsigned)h + (unsigned)y) * (unsigned)w + (unsigned)x0;
+    uint8_t* dp = dst + (size_t)blockIdx.z * stride + (size_t)y * pitch + x0;
+    unsigned v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = ef_lowbias32(seed ^ (base + i)) >> 24;
+    if (x0 + 3 < w && (reinterpret_cast<uintptr_t>(dp) & 3) == 0) *reinterpret_cast<unsigned*>(dp) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    else for (int i = 0; i < 4 && x0 + i < w; i++) dp[i] = (uint8_t)v[i];
+}
+
+extern "C" int ef_synth_frames_async(uint8_t* d_frames, size_t pitch, size_t frame_stride, int width, int height, int nframes,
+                                     unsigned seed, unsigned first_frame, void* stream)
+{
+    if (!d_frames || width <= 0 || height <= 0 || nframes <= 0 || nframes > 65535 || pitch < (size_t)width) return EF_ERR_BAD_ARG;
+    const dim3 grid(ef_div_up(ef_div_up(width, 4), 256), height, nframes);
+    ef_synth_frames_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_frames, pitch, frame_stride, width, height, seed, first_frame);
+    EF_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? EF_OK : EF_ERR_CUDA;
+}

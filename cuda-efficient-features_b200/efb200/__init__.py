@@ -38,7 +38,7 @@ EXPORTS = [
     "ef_mg_last_error_string",
     "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows",
     "ef_match_scratch_bytes", "ef_match_knn_async", "ef_match_cross_check_async", "ef_match_ratio_cross_async",
-    "ef_match_last_error_string", "ef_bgr_to_gray_async", "ef_debug_project_async",
+    "ef_match_last_error_string", "ef_bgr_to_gray_async", "ef_debug_project_async", "ef_synth_frames_async",
 ]
 STAGE_NAMES = ["pyramid", "score", "nms", "compact", "select", "angle_pack", "blur", "describe", "project"]
 
@@ -125,6 +125,7 @@ def load_library() -> C.CDLL:
     L.ef_match_last_error_string.restype = C.c_char_p
     L.ef_bgr_to_gray_async.argtypes = [vp, sz, i32, i32, i32, vp, sz, vp]
     L.ef_debug_project_async.argtypes = [vp, vp, i32, i32, vp, sz, vp]
+    L.ef_synth_frames_async.argtypes = [vp, sz, sz, i32, i32, i32, C.c_uint, C.c_uint, vp]
     _lib = L
     return L
 
@@ -607,6 +608,23 @@ class HashSIFT(_Describer):
         if nbits not in (100, 101):
             raise EfError("n_bits should be either SIZE_512_BITS or SIZE_256_BITS")
         return HashSIFT(HASH_SIFT_512 if nbits == 100 else HASH_SIFT_256, croppingScale, max_width, max_height, max_keypoints, device)
+
+
+def synth_frames(nframes: int, height: int, width: int, seed: int, first_frame: int = 0, device=None, out=None, stream=None):
+    """Synthetic uniform-noise frames of the benchmark generated ON THE DEVICE (ef_synth_frames_async): the pinned counter-based
+    generator SURVEY 8d prescribes, bit-identical to the CPU arm's (oracle synth_frame(seed, frame, w, h)).  -> F x H x W uint8."""
+    torch = _torch()
+    L = load_library()
+    if out is None:
+        out = torch.empty((nframes, height, width), dtype=torch.uint8, device=device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    if not (out.is_cuda and out.dtype == torch.uint8 and out.dim() == 3 and out.stride(2) == 1 and tuple(out.shape) == (nframes, height, width)):
+        raise EfError("out must be an F x H x W uint8 CUDA tensor")
+    with torch.cuda.device(out.device):
+        rc = L.ef_synth_frames_async(out.data_ptr(), out.stride(1), out.stride(0), width, height, nframes, seed & 0xffffffff, first_frame,
+                                     _stream_ptr(stream, out.device))
+    if rc != 0:
+        raise EfError(f"ef_synth_frames_async failed with status {rc}")
+    return out
 
 
 # ---- callers either side of the path: matcher and colour conversion (efb200/matching.py) ----

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+COLLECTIVES = "NCCL broadcast of the image, all-gather of band candidates, MAX all-reduce of the descriptor matrix"
+
 
 def band_tile_rows(tiles_y: int, shard: int, nshards: int, halo_tiles: int = 1):
     """(own0, own_n, score0, score_n): tile rows owned by `shard` and the rows its score stage covers (host arithmetic of

@@ -222,6 +222,11 @@ int ef_stage_timing_enable(ef_handle* h, int enable);
 int ef_stage_times(ef_handle* h, float* ms_sum /* [EF_NUM_STAGES] */, int* ncalls);
 /* number of kernels this library has launched in the process so far */
 unsigned long long ef_kernel_launch_count(void);
+/* synthetic uniform-noise frames of the benchmark: pix(f, y, x) = lowbias32(seed ^ ((f * H + y) * W + x)) >> 24 with
+ * f = first_frame + frame index -- the generator the CPU arm uses (oracle efo_synth_frame), on the device, so that both arms of
+ * bench.py see the same pixels.  Frame i is written at d_frames + i * frame_stride, rows `pitch` bytes apart. */
+int ef_synth_frames_async(uint8_t* d_frames, size_t pitch, size_t frame_stride, int width, int height, int nframes,
+                          unsigned seed, unsigned first_frame, void* stream);
 
 #ifdef __cplusplus
 }

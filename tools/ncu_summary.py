@@ -70,6 +70,13 @@ def main():
         res["_warp_inst"] = {st: (sum(v) if st == "pyramid" else sum(v) / len(v)) for st, v in winst.items()}
         res["_smem_wavefronts"] = {st: (sum(v) if st == "pyramid" else sum(v) / len(v)) for st, v in wavef.items()}
         res["_frames"] = int(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 8
+        # hash of the kernel sources the capture was taken from: bench.py reports the capture only while it matches
+        import hashlib
+        from pathlib import Path
+        hsh = hashlib.sha256()
+        for f in sorted((Path(__file__).resolve().parent.parent / "cuda-efficient-features_b200" / "csrc").glob("*.cu*")):
+            hsh.update(f.name.encode()); hsh.update(f.read_bytes())
+        res["_src_sha"] = hsh.hexdigest()[:16]
         res["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch group (one step of the captured bench command, _frames frames), from " + rep
         with open(traffic_path, "w") as f:
             json.dump(res, f, indent=1)
