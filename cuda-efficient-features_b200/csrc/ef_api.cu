@@ -161,6 +161,10 @@ struct ef_handle {
     size_t ev_used = 0;      // events consumed since the last ef_stage_times()
     std::vector<int> ev_stage; // stage id that ENDS at event i (-1 = start marker)
 
+    // tensor maps of the current geometry (re-encoded only when the caller's image, its layout or the frame size changes)
+    EfTmaMaps tma;
+    const void* tma_img0 = nullptr; size_t tma_stride = 0; int tma_pitch = 0, tma_w = 0, tma_h = 0, tma_nframes = 0;
+
     // last call
     int last_w = 0, last_h = 0, last_nframes = 0;
     const uint8_t* last_img0 = nullptr; size_t last_img0_stride = 0; int last_img0_pitch = 0;
@@ -533,6 +537,22 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
     return EF_OK;
 }
 
+// tensor maps over the level images of this call (ef_tma.cuh); cheap, and cached while the geometry stays the same
+const EfTmaMaps* prepare_tma(ef_handle* h, const EfPipe& P)
+{
+    if (h->tma_img0 == P.img0 && h->tma_stride == P.img0_stride && h->tma_pitch == P.img0_pitch && h->tma_w == P.lv[0].w && h->tma_h == P.lv[0].h &&
+        h->tma_nframes == P.nframes) return &h->tma;
+    h->tma.blur_src_ok = 0;
+    for (int l = P.first_level; l < P.nlevels; l++) {
+        const EfLevel& L = P.lv[l];
+        const void* base = l == 0 ? (const void*)P.img0 : (const void*)(P.ws + L.img_off);
+        const size_t pitch = l == 0 ? (size_t)P.img0_pitch : (size_t)L.img_pitch, stride = l == 0 ? (size_t)P.img0_stride : (size_t)P.ws_stride;
+        if (ef_tma_encode_u8(&h->tma.blur_src[l], base, L.w, L.h, P.nframes, pitch, stride, EF_BLUR_BOX_W, EF_BLUR_BOX_H)) h->tma.blur_src_ok |= 1u << l;
+    }
+    h->tma_img0 = P.img0; h->tma_stride = P.img0_stride; h->tma_pitch = P.img0_pitch; h->tma_w = P.lv[0].w; h->tma_h = P.lv[0].h; h->tma_nframes = P.nframes;
+    return &h->tma;
+}
+
 void mark(ef_handle* h, int stage, cudaStream_t s)
 {
     if (!h->timing) return;
@@ -561,7 +581,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
         EF_CUDA(h, cudaEventRecord(h->ev_fork, s));
         EF_CUDA(h, cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
         mark(h, -2, h->s_side);
-        ef_launch_blur(P, h->s_side); mark(h, EF_STAGE_BLUR, h->s_side);
+        ef_launch_blur(P, prepare_tma(h, P), h->s_side); mark(h, EF_STAGE_BLUR, h->s_side);
         EF_CUDA(h, cudaEventRecord(h->ev_join, h->s_side));
         mark(h, -2, s);
     }
@@ -571,7 +591,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
     ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);
     if (want_desc) {
         if (side) { EF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0)); mark(h, -2, s); }
-        else { ef_launch_blur(P, s);     mark(h, EF_STAGE_BLUR, s); }
+        else { ef_launch_blur(P, prepare_tma(h, P), s);     mark(h, EF_STAGE_BLUR, s); }
         const int v = (P.desc_bytes == 32) ? 0 : 1;
         if (is_bad(P.desc_type)) {
             EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
@@ -919,7 +939,7 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
     ef_launch_select(P, s);       mark(h, EF_STAGE_SELECT, s);    // global top-quota over the concatenated bands (raster order)
     ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);// every GPU writes the full keypoint matrix (identical everywhere)
     if (d_desc) {
-        ef_launch_blur(P, s);     mark(h, EF_STAGE_BLUR, s);
+        ef_launch_blur(P, prepare_tma(h, P), s);     mark(h, EF_STAGE_BLUR, s);
         // every GPU describes the keypoints of its own band (their windows lie in the rows it blurred); rows of other GPUs stay
         // zero: MAX all-reduce assembles the matrix
         P.desc_by_band = nshards > 1 ? 1 : 0;

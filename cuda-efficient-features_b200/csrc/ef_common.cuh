@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "../../include/ef_b200.h"
+#include "ef_tma.cuh"
 
 #define EF_HALF_PATCH 15          // HALF_PATCH_SIZE, cuda_efficient_features.cpp:34 (border mask, IC radius)
 #define EF_PATCH_SIZE 31.f        // PATCH_SIZE, cuda_efficient_features.cu:36
@@ -164,7 +165,7 @@ void ef_launch_nms(const EfPipe& p, cudaStream_t s);
 void ef_launch_compact(const EfPipe& p, cudaStream_t s);
 void ef_launch_select(const EfPipe& p, cudaStream_t s);
 void ef_launch_angle_pack(const EfPipe& p, cudaStream_t s);
-void ef_launch_blur(const EfPipe& p, cudaStream_t s);
+void ef_launch_blur(const EfPipe& p, const EfTmaMaps* maps /* nullptr: no TMA */, cudaStream_t s);
 // band-sharded single frame (ef_band_*): packed per-band candidates, merge of all bands, ownership mask of descriptor rows
 #define EF_BAND_HDR 256
 void ef_launch_band_pack(const EfPipe& p, uint8_t* cand, unsigned long long cand_stride, cudaStream_t s);

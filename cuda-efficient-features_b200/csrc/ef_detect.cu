@@ -516,8 +516,11 @@ __global__ void __launch_bounds__(256, 8) ef_score_kernel(const __grid_constant_
         //      SCALE * (float)d in the reference.
         const unsigned twou = 0x40004000u;
         const __half2 two = *reinterpret_cast<const __half2*>(&twou);
-        for (int i = tid; i < SC_GROWS * 20; i += 256) {
-            const int row = i / 20, pr = i - row * 20;      // gradient row `row` <-> tile-local row row+1; pair of columns 2pr, 2pr+1
+        // Lane mapping: a half-warp takes the 16 column pairs 0..15 of one gradient row, the two halves of a warp rows r and r + 2
+        // (staged rows are 24 words apart: 48 words = 16 banks, so the 32 lanes of every load hit 32 distinct banks, and the 8-byte
+        // stores of a half-warp cover one 128-byte line of s_grad); the four pairs 16..19 of every row follow in a short second pass.
+        // (With the plain i / 20 mapping 43 % of this stage's shared-memory wavefronts were bank conflicts.)
+        auto sobel_pair = [&](int row, int pr) {
             const unsigned* hm = &s_h0[row][SC_PAD / 2 + pr];
             const unsigned* sm1 = &s_h1[row][SC_PAD / 2 + pr];
 #define H2(u) (*reinterpret_cast<const __half2*>(&(u)))
@@ -533,7 +536,14 @@ __global__ void __launch_bounds__(256, 8) ef_score_kernel(const __grid_constant_
             const unsigned ux = *reinterpret_cast<const unsigned*>(&dx2), uy = *reinterpret_cast<const unsigned*>(&dy2);
             // (dx, dy) of the first pixel, (dx, dy) of the second
             *reinterpret_cast<uint2*>(&s_grad[row][2 * pr]) = make_uint2(__byte_perm(ux, uy, 0x5410), __byte_perm(ux, uy, 0x7632));
+        };
+#pragma unroll
+        for (int it = 0; it < 3; it++) {
+            const int j = warp + 8 * it;                        // 20 warp-steps of two rows each cover the 38 gradient rows (+ 2 unused)
+            const int row = 4 * (j >> 1) + (j & 1) + 2 * (lane >> 4);
+            if (j < 20 && row < SC_GROWS) sobel_pair(row, lane & 15);
         }
+        if (tid < SC_GROWS * 4) sobel_pair(tid >> 2, 16 + (tid & 3));
         __syncthreads();
         // ---- Harris, raster order over the 7x7 block with the reference's contraction:
         //      g = SCALE * (float)d; sxx = fmaf(gx,gx,sxx), sxy = fmaf(gx,gy,sxy), syy = fmaf(gy,gy,syy) per tap.  (gx, gy) is one
@@ -1255,17 +1265,23 @@ void ef_launch_angle_pack(const EfPipe& p, cudaStream_t s)
 // =================================================================================================
 #define BL_TW 64
 #define BL_TH 64
-#define BL_IW 18 // words per staged input row: columns x0-4 .. x0+67
+#define BL_IW (EF_BLUR_BOX_W / 4) // words per staged input row: columns x0-16 .. x0+79 (words 3 .. 20 are used; the rest is there for the 16-byte rules of the TMA box)
+static_assert(EF_BLUR_BOX_H == BL_TH + 6 && EF_BLUR_BOX_W >= BL_TW + 20, "blur box = tile + 3 rows / 4 + 4 columns of halo");
 __device__ __forceinline__ float ef_byte_to_float(unsigned word, int i)
 {
     const unsigned m = __byte_perm(word, 0x4B000000u, 0x7540 + i);
     return __uint_as_float(m) - 8388608.f;
 }
 
-__global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__ EfPipe p)
+// TMA: interior tiles (every source row and column of the 70 x 72 window inside the image) are staged by ONE elected thread with
+// cp.async.bulk.tensor (UTMALDG) onto an mbarrier; tiles that touch an image edge keep the explicit REFLECT_101 loop.
+template <bool TMA>
+__global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__ EfTmaMaps maps /* first: tensor maps must lie in the first 4 KB of the parameter space */,
+                                                         const __grid_constant__ EfPipe p)
 {
-    __shared__ unsigned s_in[BL_TH + 6][BL_IW];
+    __shared__ __align__(128) unsigned s_in[BL_TH + 6][BL_IW];
     __shared__ __align__(16) float s_row[BL_TH + 6][BL_TW];
+    __shared__ __align__(8) unsigned long long s_mbar;
 
     const float t0 = __uint_as_float(0x3d8fafb1u), t1 = __uint_as_float(0x3e06387eu), t2 = __uint_as_float(0x3e434a39u),
                 t3 = __uint_as_float(0x3e5d4ae0u);
@@ -1280,29 +1296,41 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
     const bool fast = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0 && x0 >= 4 && x0 + BL_TW + 4 <= L.w;
+    const bool tma = TMA && fast && y0 >= 3 && y0 + BL_TH + 3 <= L.h && ((maps.blur_src_ok >> level) & 1u);   // CTA-uniform
 
-#pragma unroll
-    for (int it = 0; it < ((BL_TH + 6) * BL_IW + 255) / 256; it++) {
-        const int i = tid + 256 * it;
-        if (i >= (BL_TH + 6) * BL_IW) break;
-        const int ly = i / BL_IW, wx = i - ly * BL_IW;
-        const int gy = ef_reflect101(min(y0 - 3 + ly, L.h + 2), L.h);
-        const uint8_t* rp = img + (size_t)gy * pitch;
-        const int gx = x0 - 4 + 4 * wx;
-        unsigned word;
-        if (fast) word = *reinterpret_cast<const unsigned*>(rp + gx);
-        else {
-            word = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) word |= (unsigned)rp[ef_reflect101(min(gx + j, L.w + 2), L.w)] << (8 * j);
+    if (tma) {
+        const unsigned mbar = ef_smem_addr(&s_mbar);
+        if (tid == 0) {
+            ef_mbar_init(mbar, 1);
+            ef_mbar_expect_tx(mbar, EF_BLUR_BOX_W * EF_BLUR_BOX_H);
+            ef_tma_load_3d(ef_smem_addr(&s_in[0][0]), &maps.blur_src[level], x0 - 16, y0 - 3, frame, mbar);
         }
-        s_in[ly][wx] = word;
+        __syncthreads();                    // the barrier's initialisation is visible to every waiter
+        ef_mbar_wait(mbar, 0);
+    } else {
+#pragma unroll
+        for (int it = 0; it < ((BL_TH + 6) * 18 + 255) / 256; it++) {
+            const int i = tid + 256 * it;
+            if (i >= (BL_TH + 6) * 18) break;
+            const int ly = i / 18, wx = i - ly * 18;
+            const int gy = ef_reflect101(min(y0 - 3 + ly, L.h + 2), L.h);
+            const uint8_t* rp = img + (size_t)gy * pitch;
+            const int gx = x0 - 4 + 4 * wx;
+            unsigned word;
+            if (fast) word = *reinterpret_cast<const unsigned*>(rp + gx);
+            else {
+                word = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) word |= (unsigned)rp[ef_reflect101(min(gx + j, L.w + 2), L.w)] << (8 * j);
+            }
+            s_in[ly][3 + wx] = word;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // row pass: output columns 4c .. 4c+3 need input columns 4c-3 .. 4c+6 = staged bytes 4c+1 .. 4c+10
+    // row pass: output columns 4c .. 4c+3 need input columns 4c-3 .. 4c+6 = staged bytes 4c+13 .. 4c+22 (staged byte 0 = column x0-16)
     for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4); i += 256) {
         const int ly = i >> 4, c = i & 15;
-        const unsigned w0 = s_in[ly][c], w1 = s_in[ly][c + 1], w2 = s_in[ly][c + 2];
+        const unsigned w0 = s_in[ly][c + 3], w1 = s_in[ly][c + 4], w2 = s_in[ly][c + 5];
         // packed fp32 (fma.rn.f32x2, per-lane IEEE = the scalar chain): outputs (0,1) and (2,3) advance together; tap k multiplies the
         // input pair (k, k+1) resp. (k+2, k+3).  Pairs starting at an even / odd input are converted separately (E[m] = inputs 2m,
         // 2m+1; O[m] = inputs 2m+1, 2m+2) so that every pair is born in an aligned register pair.
@@ -1355,10 +1383,13 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     }
 }
 
-void ef_launch_blur(const EfPipe& p, cudaStream_t s)
+void ef_launch_blur(const EfPipe& p, const EfTmaMaps* maps, cudaStream_t s)
 {
     if (p.total_blur_tiles <= 0) return;
-    ef_blur_kernel<<<dim3(p.total_blur_tiles, p.nframes), 256, 0, s>>>(p);
+    static const bool use_tma = !(getenv("EF_BLUR_TMA") && atoi(getenv("EF_BLUR_TMA")) == 0);   // A/B switch; default: TMA staging
+    static const EfTmaMaps none = {};
+    if (maps && use_tma && maps->blur_src_ok) ef_blur_kernel<true><<<dim3(p.total_blur_tiles, p.nframes), 256, 0, s>>>(*maps, p);
+    else ef_blur_kernel<false><<<dim3(p.total_blur_tiles, p.nframes), 256, 0, s>>>(none, p);
     EF_COUNT_LAUNCH(1);
 }
 
