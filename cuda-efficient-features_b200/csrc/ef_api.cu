@@ -542,7 +542,19 @@ const EfTmaMaps* prepare_tma(ef_handle* h, const EfPipe& P)
 {
     if (h->tma_img0 == P.img0 && h->tma_stride == P.img0_stride && h->tma_pitch == P.img0_pitch && h->tma_w == P.lv[0].w && h->tma_h == P.lv[0].h &&
         h->tma_nframes == P.nframes) return &h->tma;
-    h->tma.blur_src_ok = 0;
+    h->tma.blur_src_ok = 0; h->tma.resize_src_ok = 0;
+    for (int l = 1; l < P.nlevels; l++) {
+        // source of pyramid level l = level l-1.  The TMA kernel zero-fills what lies outside the source instead of clamping the
+        // x2 / y2 taps (resize arithmetic: SURVEY Appendix A.1); that is exact iff no tap of the level ever clamps, i.e. iff
+        // floor((w-1) * rx) + 1 <= src_w - 1 and the same for rows -- true for every down-scaling ratio, checked here in the
+        // kernel's own float arithmetic.
+        const EfLevel& L = P.lv[l];
+        const EfLevel& S = P.lv[l - 1];
+        const bool noclamp = (int)std::floor((float)(L.w - 1) * L.rx) + 1 <= S.w - 1 && (int)std::floor((float)(L.h - 1) * L.ry) + 1 <= S.h - 1;
+        const void* base = l == 1 ? (const void*)P.img0 : (const void*)(P.ws + S.img_off);
+        const size_t pitch = l == 1 ? (size_t)P.img0_pitch : (size_t)S.img_pitch, stride = l == 1 ? (size_t)P.img0_stride : (size_t)P.ws_stride;
+        if (noclamp && ef_tma_encode_u8(&h->tma.resize_src[l], base, S.w, S.h, P.nframes, pitch, stride, EF_RS_BOX_W, EF_RS_BOX_H)) h->tma.resize_src_ok |= 1u << l;
+    }
     for (int l = P.first_level; l < P.nlevels; l++) {
         const EfLevel& L = P.lv[l];
         const void* base = l == 0 ? (const void*)P.img0 : (const void*)(P.ws + L.img_off);
@@ -571,7 +583,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
     EF_CUDA(h, cudaMemset2DAsync(h->d_ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
     EF_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
     mark(h, -1, s);
-    ef_launch_pyramid(P, s);      mark(h, EF_STAGE_PYRAMID, s);
+    ef_launch_pyramid(P, prepare_tma(h, P), s);      mark(h, EF_STAGE_PYRAMID, s);
     ef_launch_score(P, s);        mark(h, EF_STAGE_SCORE, s);
     // The blur depends on the pyramid only.  It is forked onto the side stream after the score stage (which saturates the GPU on its
     // own) and runs next to NMS, compaction, selection and angles -- latency-bound launches that leave issue slots free; the
@@ -902,7 +914,7 @@ int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, cons
     EF_CUDA(h, cudaMemset2DAsync(h->d_ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
     EF_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
     mark(h, -1, s);
-    ef_launch_pyramid(P, s);      mark(h, EF_STAGE_PYRAMID, s);   // whole pyramid on every GPU: the halo of level s would need level s-1's anyway
+    ef_launch_pyramid(P, prepare_tma(h, P), s);      mark(h, EF_STAGE_PYRAMID, s);   // whole pyramid on every GPU: the halo of level s would need level s-1's anyway
     ef_launch_score(P, s);        mark(h, EF_STAGE_SCORE, s);     // owned tile rows + NMS halo
     ef_launch_nms(P, s);          mark(h, EF_STAGE_NMS, s);       // owned tile rows
     ef_launch_compact(P, s);      mark(h, EF_STAGE_COMPACT, s);

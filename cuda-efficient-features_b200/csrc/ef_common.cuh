@@ -159,7 +159,7 @@ extern unsigned long long g_ef_launches;
 #define EF_COUNT_LAUNCH(n) ((void)__atomic_fetch_add(&g_ef_launches, (unsigned long long)(n), __ATOMIC_RELAXED)) // host threads of ef_mg_*
 
 // ---- launchers (host) ----------------------------------------------------------------------------
-void ef_launch_pyramid(const EfPipe& p, cudaStream_t s);
+void ef_launch_pyramid(const EfPipe& p, const EfTmaMaps* maps /* nullptr: no TMA */, cudaStream_t s);
 void ef_launch_score(const EfPipe& p, cudaStream_t s);
 void ef_launch_nms(const EfPipe& p, cudaStream_t s);
 void ef_launch_compact(const EfPipe& p, cudaStream_t s);

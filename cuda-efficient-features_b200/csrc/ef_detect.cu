@@ -341,22 +341,169 @@ __global__ void __launch_bounds__(256, 4) ef_resize_tiled16_kernel(const __grid_
     }
 }
 
-static const bool g_ef_resize_legacy = getenv("EF_RESIZE") && !strcmp(getenv("EF_RESIZE"), "legacy");
-void ef_launch_pyramid(const EfPipe& p, cudaStream_t s)
+// TMA form of the tiled kernel (same tile, same warp / lane / row mapping, same tap arithmetic): the u8 source window is staged by
+// ONE cp.async.bulk.tensor.3d (UTMALDG) -- no staging loop, no u8 -> fp32 conversion pass, 13.7 KB instead of 56 KB of shared memory --
+// and every lane reads the <= 6 source bytes its four output pixels need from a source row as three aligned words, funnel-shifted
+// to the first needed byte; two byte permutes with per-lane selectors (computed once) pick the four left and the four right taps,
+// which are then expanded to fp32 (0x4B0000bb = 2^23 + b, packed subtract).  Against the fp32 window: 3 word loads per lane and
+// source row at a 4.8-byte lane stride (mostly distinct banks) instead of 8 tap loads at a 4.8-WORD stride (2-way conflicts).
+// Needs a 16-byte aligned source (base, pitch, frame stride) and a level whose taps never clamp at the right / bottom edge (any
+// down-scaling ratio: checked exactly on the host); otherwise ef_resize_tiled16_kernel runs.
+#define RS4_PITCH EF_RS_BOX_W
+#define RS4_SMEM (EF_RS_BOX_H * EF_RS_BOX_W + 16 + RS3_TH * 16 + 16)
+
+template <int NB>   // resident CTAs per SM the register allocation aims at (4 / 5 / 6 measured: 0.253 / 0.249 / 0.245 ms per 16 frames)
+__global__ void __launch_bounds__(256, NB) ef_resize_tma_kernel(const __grid_constant__ EfTmaMaps maps, const __grid_constant__ EfPipe p, const int level)
 {
+    extern __shared__ __align__(128) unsigned char s_raw4[];
+    unsigned char* __restrict__ s_u8 = s_raw4;                                                        // [78][176] + 16 bytes of slack
+    EfRowGeo* __restrict__ s_row = reinterpret_cast<EfRowGeo*>(s_raw4 + EF_RS_BOX_H * EF_RS_BOX_W + 16);
+    unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_raw4 + EF_RS_BOX_H * EF_RS_BOX_W + 16 + RS3_TH * 16);
+
+    const EfLevel& L = p.lv[level];
+    const int frame = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * RS3_TW, Y0 = blockIdx.y * RS3_TH;
+    const int sx0 = __float2int_rd((float)X0 * L.rx) & ~15;
+    const int sy0 = __float2int_rd((float)Y0 * L.ry);
+
+    const unsigned mbar = ef_smem_addr(s_mbar);
+    if (tid == 0) {
+        ef_mbar_init(mbar, 1);
+        ef_mbar_expect_tx(mbar, EF_RS_BOX_W * EF_RS_BOX_H);
+        // programmatic dependent launch: this grid may have been scheduled while the previous level's grid was still draining;
+        // its output (our source) is complete once this returns (no-op for a normally serialised launch)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        ef_tma_load_3d(ef_smem_addr(s_u8), &maps.resize_src[level], sx0, sy0, frame, mbar);
+    }
+    // row geometry of the tile's output rows while the window is in flight
+    if (tid < RS3_TH) {
+        const int y = min(Y0 + tid, L.h - 1);
+        const float sy = (float)y * L.ry;
+        const int y1 = __float2int_rd(sy);
+        const int yp = min(Y0 + tid - 1, L.h - 1);
+        const int offp = min(__float2int_rd((float)yp * L.ry) - sy0, EF_RS_BOX_H - 2) * RS4_PITCH;
+        EfRowGeo g;
+        g.off = min(y1 - sy0, EF_RS_BOX_H - 2) * RS4_PITCH; // bytes
+        g.wy1 = (float)(y1 + 1) - sy; g.wy2 = sy - (float)y1;
+        g.reload = ((tid & 7) == 0 || g.off != offp + RS4_PITCH) ? 1 : 0;
+        s_row[tid] = g;
+    }
+    __syncthreads();                    // mbarrier initialised, row table written
+    ef_mbar_wait(mbar, 0);
+
+    const int x0 = X0 + 4 * lane;
+    if (x0 >= L.w) return;
+    int o[4];
+    float wx1[4], wx2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = min(x0 + j, L.w - 1);
+        const float sx = (float)x * L.rx;
+        const int x1 = __float2int_rd(sx);
+        o[j] = min(x1 - sx0, EF_RS_BOX_W - 2);
+        wx1[j] = (float)(x1 + 1) - sx; wx2[j] = sx - (float)x1;
+    }
+    const unsigned long long wx1a = ef_pack2(wx1[0], wx1[1]), wx1b = ef_pack2(wx1[2], wx1[3]);
+    const unsigned long long wx2a = ef_pack2(wx2[0], wx2[1]), wx2b = ef_pack2(wx2[2], wx2[3]);
+    // byte window of the lane: starts at o[0]; left taps at o[j] - o[0] in 0..4, right taps one further (<= 5)
+    const int wb = o[0] & ~3;
+    const unsigned sh = 8u * (unsigned)(o[0] & 3);
+    unsigned selL = 0, selR = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned d = (unsigned)min(max(o[j] - o[0], 0), 6);   // 0..4 for real pixels; clamped copies of the last column stay in range
+        selL |= d << (4 * j); selR |= (d + 1) << (4 * j);
+    }
+    const unsigned char* wbase = s_u8 + wb;
+    const unsigned long long m23 = ef_pack2(-8388608.f, -8388608.f);
+
+    const int r0 = (RS3_TH / 8) * warp;
+    const int nr = min(RS3_TH / 8, L.h - (Y0 + r0));
+    uint8_t* dst = ef_ws(p, frame, L.img_off) + (size_t)(Y0 + r0) * L.img_pitch + x0;
+    const size_t dpitch = (size_t)L.img_pitch;
+
+    auto load_taps = [&](EfTaps& t, int offb) {
+        const unsigned* wp = reinterpret_cast<const unsigned*>(wbase + offb);
+        const unsigned W0 = wp[0], W1 = wp[1], W2 = wp[2];
+        const unsigned A = __funnelshift_r(W0, W1, sh), B = __funnelshift_r(W1, W2, sh);   // bytes o[0] .. o[0]+7 of the row
+        const unsigned tl = __byte_perm(A, B, selL), tr = __byte_perm(A, B, selR);
+#define RS4_F(wd, i) __uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7540 + (i)))
+        t.a0 = ef_add2(ef_pack2(RS4_F(tl, 0), RS4_F(tl, 1)), m23); t.b0 = ef_add2(ef_pack2(RS4_F(tl, 2), RS4_F(tl, 3)), m23);
+        t.a1 = ef_add2(ef_pack2(RS4_F(tr, 0), RS4_F(tr, 1)), m23); t.b1 = ef_add2(ef_pack2(RS4_F(tr, 2), RS4_F(tr, 3)), m23);
+#undef RS4_F
+    };
+    auto emit_row = [&](const EfTaps& top, const EfTaps& bot, const EfRowGeo& g) {
+        const unsigned long long wy1p = ef_pack2(g.wy1, g.wy1), wy2p = ef_pack2(g.wy2, g.wy2);
+        // tap order = ef_resize_kernel: (y1,x1) (y1,x2) (y2,x1) (y2,x2)
+        unsigned long long a = ef_mul2(top.a0, ef_mul2(wx1a, wy1p));
+        unsigned long long b = ef_mul2(top.b0, ef_mul2(wx1b, wy1p));
+        a = ef_fma2(top.a1, ef_mul2(wx2a, wy1p), a);
+        b = ef_fma2(top.b1, ef_mul2(wx2b, wy1p), b);
+        a = ef_fma2(bot.a0, ef_mul2(wx1a, wy2p), a);
+        b = ef_fma2(bot.b0, ef_mul2(wx1b, wy2p), b);
+        a = ef_fma2(bot.a1, ef_mul2(wx2a, wy2p), a);
+        b = ef_fma2(bot.b1, ef_mul2(wx2b, wy2p), b);
+        float o0, o1, o2, o3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(a));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o2), "=f"(o3) : "l"(b));
+        const unsigned packed = __byte_perm(__byte_perm(ef_sat_u8_rne(o0), ef_sat_u8_rne(o1), 0x0040), __byte_perm(ef_sat_u8_rne(o2), ef_sat_u8_rne(o3), 0x0040), 0x5410);
+        *reinterpret_cast<unsigned*>(dst) = packed; // img_pitch is a multiple of 128
+        dst += dpitch;
+    };
+    EfTaps X, Y;
+#pragma unroll
+    for (int r = 0; r < RS3_TH / 8; r += 2) {
+        if (r >= nr) break;
+        {
+            const EfRowGeo g = s_row[r0 + r];
+            if (g.reload) load_taps(X, g.off);              // warp-uniform
+            load_taps(Y, g.off + RS4_PITCH);
+            emit_row(X, Y, g);
+        }
+        if (r + 1 >= nr) break;
+        {
+            const EfRowGeo g = s_row[r0 + r + 1];
+            if (g.reload) load_taps(Y, g.off);
+            load_taps(X, g.off + RS4_PITCH);
+            emit_row(Y, X, g);
+        }
+    }
+}
+
+static const bool g_ef_resize_legacy = getenv("EF_RESIZE") && !strcmp(getenv("EF_RESIZE"), "legacy");
+void ef_launch_pyramid(const EfPipe& p, const EfTmaMaps* maps, cudaStream_t s)
+{
+    static const bool use_tma = !(getenv("EF_RESIZE_TMA") && atoi(getenv("EF_RESIZE_TMA")) == 0);   // A/B switch; default: TMA staging
+    bool tma_prev = false;   // the previous launch of this chain was the TMA kernel (which contains the griddepcontrol.wait)
     for (int l = 1; l < p.nlevels; l++) {
         const bool src16 = l > 1 || ((reinterpret_cast<uintptr_t>(p.img0) | p.img0_stride | (unsigned long long)p.img0_pitch) & 15ull) == 0;
-        if (src16 && p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.22f && !g_ef_resize_legacy) {
-            // the attribute is per device (ef_mg_* drives several devices from one process): one bit per device
-            static unsigned long long configured = 0;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (!((__atomic_load_n(&configured, __ATOMIC_RELAXED) >> (dev & 63)) & 1ull)) {
-                cudaFuncSetAttribute(ef_resize_tiled16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS3_SMEM);
-                __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
-            }
+        // the attribute is per device (ef_mg_* drives several devices from one process): one bit per device
+        static unsigned long long configured = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((__atomic_load_n(&configured, __ATOMIC_RELAXED) >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(ef_resize_tiled16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS3_SMEM);
+            __atomic_fetch_or(&configured, 1ull << (dev & 63), __ATOMIC_RELAXED);
+        }
+        if (maps && use_tma && ((maps->resize_src_ok >> l) & 1u) && p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.22f && !g_ef_resize_legacy) {
+            const dim3 grid(ef_div_up(p.lv[l].w, RS3_TW), ef_div_up(p.lv[l].h, RS3_TH), p.nframes);
+            // levels >= 2 follow another resize launch: programmatic dependent launch hides the launch gap of the 7-deep chain
+            static const bool pdl = !(getenv("EF_RESIZE_PDL") && atoi(getenv("EF_RESIZE_PDL")) == 0);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = RS4_SMEM; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = (pdl && l >= 2 && tma_prev) ? 1 : 0;
+            cudaLaunchKernelEx(&cfg, ef_resize_tma_kernel<6>, *maps, p, l);
+            tma_prev = true;
+            EF_COUNT_LAUNCH(1);
+            continue;
+        } else if (src16 && p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.22f && !g_ef_resize_legacy) {
             const dim3 grid(ef_div_up(p.lv[l].w, RS3_TW), ef_div_up(p.lv[l].h, RS3_TH), p.nframes);
             ef_resize_tiled16_kernel<<<grid, 256, RS3_SMEM, s>>>(p, l);
+            tma_prev = false;
         } else if (p.lv[l].rx <= 1.21f && p.lv[l].ry <= 1.25f) {
             const dim3 grid(ef_div_up(p.lv[l].w, RS_TW), ef_div_up(p.lv[l].h, RS_TH), p.nframes);
             ef_resize_tiled_kernel<<<grid, 256, 0, s>>>(p, l);

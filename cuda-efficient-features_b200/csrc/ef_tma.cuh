@@ -16,10 +16,15 @@
 #define EF_BLUR_BOX_W 96   // bytes per staged row: columns x0-16 .. x0+79 (inner box extent AND inner start coordinate must be multiples of 16 bytes)
 #define EF_BLUR_BOX_H 70   // rows y0-3 .. y0+66
 
+#define EF_RS_BOX_W 176    // source window of one 128 x 64 resize tile: <= 176 columns from a 16-byte aligned start ...
+#define EF_RS_BOX_H 78     // ... and <= 78 rows (ratios <= 1.21 x 1.22)
+
 struct alignas(64) EfTmaMaps {
     CUtensorMap blur_src[EF_MAX_LEVELS];   // level images, box EF_BLUR_BOX_W x EF_BLUR_BOX_H x 1 (input of the Gaussian blur)
+    CUtensorMap resize_src[EF_MAX_LEVELS]; // [l] = level l-1 image, box EF_RS_BOX_W x EF_RS_BOX_H x 1 (source of pyramid level l)
     unsigned blur_src_ok;                  // bit l: blur_src[l] is valid (base / strides 16-byte aligned)
-    unsigned pad_[15];
+    unsigned resize_src_ok;                // bit l: resize_src[l] is valid AND level l never clamps a tap (see ef_api.cu)
+    unsigned pad_[14];
 };
 
 // host: encode a map over `nframes` pitched u8 images; false when the layout does not meet the TMA alignment rules
