@@ -33,6 +33,17 @@ extern "C" void ef_band_tile_rows(int tiles_y, int shard, int nshards, int halo_
     *score0 = sa; *score_n = sb - sa;
 }
 
+// Output rows of the descriptor matrix that band `shard` of `nshards` fills (ef_band_finish_async): equal blocks of
+// ceil(nfeatures / nshards) rows, so that an all-gather of fixed-size blocks assembles the matrix.  Pure host arithmetic.
+extern "C" void ef_band_desc_rows(int nfeatures, int shard, int nshards, int* row0, int* nrows)
+{
+    if (nshards < 1) nshards = 1;
+    if (shard < 0) shard = 0;
+    if (shard >= nshards) shard = nshards - 1;
+    const int c = (std::max(nfeatures, 0) + nshards - 1) / nshards;
+    *row0 = shard * c; *nrows = c;
+}
+
 namespace {
 
 struct Geometry {
@@ -116,6 +127,7 @@ struct ef_handle {
 
     uint8_t* d_ws = nullptr;
     EfLevelCounters* d_counters = nullptr;
+    int* d_slice_y = nullptr;       // [max_batch][EF_MAX_LEVELS][2]: row span of this GPU's descriptor slice per level (ef_band_finish_async)
 
     // descriptor tables (per handle, per device)
     uchar4* d_bad_boxes[2] = { nullptr, nullptr };
@@ -216,7 +228,7 @@ int quota_sum(const ef_params& p)
 
 void free_all(ef_handle* h)
 {
-    cudaFree(h->d_ws); cudaFree(h->d_counters);
+    cudaFree(h->d_ws); cudaFree(h->d_counters); cudaFree(h->d_slice_y);
     for (int i = 0; i < 2; i++) { cudaFree(h->d_bad_boxes[i]); cudaFree(h->d_bad_radius[i]); cudaFree(h->d_bad_thr[i]); cudaFree(h->d_hs_weights_t[i]); cudaFree(h->d_hs_bfrag[i]); cudaFree(h->d_hs_btc[i]); cudaFree(h->d_hs_bias[i]); }
     cudaFree(h->d_exp_table); cudaFree(h->d_grad_table); cudaFree(h->d_sift128); cudaFree(h->d_proj);
     cudaFree(h->d_integral); cudaFree(h->d_segsum); cudaFree(h->d_kpts4);
@@ -438,6 +450,7 @@ int allocate(ef_handle* h)
         // row padding (columns w .. pitch) is read by the 16-byte window loads but never written: define it once
         EF_CUDA(h, cudaMemset(h->d_ws, 0, (size_t)h->slot_bytes * p.max_batch));
         EF_CUDA(h, alloc((void**)&h->d_counters, sizeof(EfLevelCounters) * EF_MAX_LEVELS * p.max_batch));
+        EF_CUDA(h, alloc((void**)&h->d_slice_y, sizeof(int) * 2 * EF_MAX_LEVELS * p.max_batch));
     }
     h->sift_rows = conly ? (size_t)p.max_keypoints : std::max((size_t)p.max_batch * p.nfeatures, (size_t)p.max_keypoints);
     EF_CUDA(h, alloc((void**)&h->d_sift128, h->sift_rows * 128));
@@ -489,7 +502,8 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
     const NmsGeom ng = nms_geometry(p.nonmax_radius);
     P.fast_threshold = p.fast_threshold; P.nms_r2 = ng.r2; P.nms_R = ng.R; P.nms_block = ng.block; P.nms_K = ng.K;
     P.nfeatures = p.nfeatures;
-    P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0; P.desc_by_band = 0;
+    P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0;
+    P.desc_row0 = 0; P.desc_rows = 0x7fffffff; P.blur_by_slice = 0; P.slice_y = h->d_slice_y;
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
     P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
     P.counters = h->d_counters;
@@ -951,12 +965,24 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
     ef_launch_select(P, s);       mark(h, EF_STAGE_SELECT, s);    // global top-quota over the concatenated bands (raster order)
     ef_launch_angle_pack(P, s);   mark(h, EF_STAGE_ANGLE_PACK, s);// every GPU writes the full keypoint matrix (identical everywhere)
     if (d_desc) {
+        // Descriptors: this GPU fills output rows [row0, row0 + nrows) (ef_band_desc_rows), the caller all-gathers the equal row
+        // blocks in place.  The blur covers every level again (the slice cuts across levels), but each tile first checks whether
+        // a window of an owned keypoint can touch it (ef_band_slice_ranges_kernel).
+        int row0 = 0, nrows = 0;
+        ef_band_desc_rows(h->prm.nfeatures, shard, nshards, &row0, &nrows);
+        P.desc_row0 = row0; P.desc_rows = nrows;
+        if (nshards > 1) {
+            int btiles = 0;
+            for (int l = 0; l < P.nlevels; l++) {
+                EfLevel& L = P.lv[l];
+                L.blur_ty0 = 0; L.blur_rows = ef_div_up(L.h, 64); L.blur_tile_start = btiles;
+                if (l >= P.first_level) btiles += L.blur_tiles_x * L.blur_rows;
+            }
+            P.total_blur_tiles = btiles;
+            P.blur_by_slice = 1;
+            ef_launch_band_slice_ranges(P, h->d_slice_y, s);
+        }
         ef_launch_blur(P, prepare_tma(h, P), s);     mark(h, EF_STAGE_BLUR, s);
-        // every GPU describes the keypoints of its own band (their windows lie in the rows it blurred); rows of other GPUs stay
-        // zero: MAX all-reduce assembles the matrix
-        P.desc_by_band = nshards > 1 ? 1 : 0;
-        for (int f = 0; f < nframes; f++)
-            EF_CUDA(h, cudaMemset2DAsync(d_desc + f * desc_stride, desc_pitch, 0, (size_t)db, (size_t)h->prm.nfeatures, s));
         const int v = (db == 32) ? 0 : 1;
         if (is_bad(P.desc_type)) {
             EfBadTables t{ h->d_bad_boxes[v], h->d_bad_radius[v], h->d_bad_thr[v] };
@@ -966,10 +992,10 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
             EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
+            // the projection runs over all rows: rows of other GPUs come out of stale SIFT vectors and are overwritten by the all-gather
             const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
             ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, db * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, nullptr, s);
-            if (nshards > 1) ef_launch_band_mask_rows(P, true, s);
             mark(h, EF_STAGE_PROJECT, s);
         }
     }

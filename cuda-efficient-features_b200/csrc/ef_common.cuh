@@ -64,7 +64,10 @@ struct EfPipe {
     int nfeatures;              // output capacity (columns)
     int desc_type, desc_bytes;
     int shard_i, shard_n;       // descriptor CTAs dealt round-robin to shard_n GPUs (unused by ef_band_*: kept for callers that shard by CTA); 0, 1 otherwise
-    int desc_by_band;           // ef_band_finish_async: describe only the keypoints whose tile row lies in [own_ty0, own_ty0 + own_rows)
+    // ef_band_finish_async: this GPU describes the keypoints of output rows [desc_row0, desc_row0 + desc_rows) only (whole matrix otherwise);
+    // blur_by_slice: the blur skips the tiles none of their windows can touch (slice_y[frame][level] = {first row - 24, last row + 24})
+    int desc_row0, desc_rows, blur_by_slice;
+    const int* slice_y;
     int select_from_counters;   // select stage: candidate count comes from counters[].overflow (merged band candidates), not from rowcnt
     // caller buffers (frame f at base + f*stride)
     const uint8_t* img0; unsigned long long img0_stride; int img0_pitch;
@@ -170,7 +173,7 @@ void ef_launch_blur(const EfPipe& p, const EfTmaMaps* maps /* nullptr: no TMA */
 #define EF_BAND_HDR 256
 void ef_launch_band_pack(const EfPipe& p, uint8_t* cand, unsigned long long cand_stride, cudaStream_t s);
 void ef_launch_band_merge(const EfPipe& p, const uint8_t* all, unsigned long long cand_stride, int nshards, cudaStream_t s);
-void ef_launch_band_mask_rows(const EfPipe& p, bool hashsift, cudaStream_t s);
+void ef_launch_band_slice_ranges(const EfPipe& p, int* slice_y, cudaStream_t s);
 
 // descriptor stage: keypoints either from the per-level selected lists (detectAndCompute) or from a
 // flat caller array (compute-only API)

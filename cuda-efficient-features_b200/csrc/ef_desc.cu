@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_pipe_kernel(const _
     const int row = offset + i;
     if (row >= p.nfeatures) return;
 
+    if ((unsigned)(row - p.desc_row0) >= (unsigned)p.desc_rows) return;   // band-sharded frame: another GPU's output row (warp-uniform)
     const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[i];
-    if (p.desc_by_band && (unsigned)((k.y >> 5) - L.own_ty0) >= (unsigned)L.own_rows) return;   // another band's keypoint (warp-uniform)
     const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
     const int pitch = L.blur_pitch;
     unsigned* __restrict__ W = s_win_all + warp * ((EF_BW_ROWS + 1) * EF_BW_WORDS);

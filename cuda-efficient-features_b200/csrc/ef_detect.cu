@@ -1440,6 +1440,11 @@ __global__ void __launch_bounds__(256, 6) ef_blur_kernel(const __grid_constant__
     const int t = blockIdx.x - L.blur_tile_start;
     const int tyl = ef_div_fast(t, L.blur_tiles_x, L.blur_tiles_x_inv), tyi = tyl + L.blur_ty0;
     const int x0 = (t - tyl * L.blur_tiles_x) * BL_TW, y0 = tyi * BL_TH;
+    if (p.blur_by_slice) {
+        // band-sharded frame: only the rows a descriptor window of an owned keypoint can touch (CTA-uniform exit)
+        const int lo = p.slice_y[(frame * EF_MAX_LEVELS + level) * 2], hi = p.slice_y[(frame * EF_MAX_LEVELS + level) * 2 + 1];
+        if (y0 + BL_TH <= lo || y0 > hi) return;
+    }
     int pitch;
     const uint8_t* __restrict__ img = ef_level_image(p, frame, level, pitch);
     const bool fast = ((reinterpret_cast<uintptr_t>(img) | (unsigned)pitch) & 3u) == 0 && x0 >= 4 && x0 + BL_TW + 4 <= L.w;
@@ -1602,24 +1607,29 @@ __global__ void __launch_bounds__(256) ef_band_merge_kernel(const __grid_constan
     }
 }
 
-// zero the descriptor rows of keypoints owned by another band (the projection ran over all rows; their SIFT vectors were not
-// computed here), so that an element-wise MAX all-reduce of the descriptor matrices assembles the frame's descriptors
-__global__ void __launch_bounds__(256) ef_band_mask_rows_kernel(const __grid_constant__ EfPipe p)
+// Descriptor ownership of a band-sharded frame is by OUTPUT ROW: GPU g describes rows [g C, (g + 1) C), C = ceil(nfeatures / N)
+// (ef_band_desc_rows), so that an in-place all-gather of equal, contiguous row blocks assembles the matrix -- no reduction, no
+// zero fill, 1/N of the bytes per GPU.  Rows are ordered by level, then raster: the slice of a GPU is, per level, a contiguous run
+// of keypoints whose rows y span [first.y, last.y].  This kernel leaves that span (+- the 24-pixel reach of a descriptor window)
+// per (frame, level) so that the blur only computes the 64-row tiles a window of an owned keypoint can touch.
+__global__ void __launch_bounds__(32) ef_band_slice_ranges_kernel(const __grid_constant__ EfPipe p, int* __restrict__ slice_y)
 {
-    const int frame = blockIdx.y;
-    const int chunks = p.desc_bytes / 16;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    const int row = idx / chunks, ch = idx - row * chunks;
-    if (row >= min(p.counts[frame], p.nfeatures)) return;
+    const int frame = blockIdx.x, level = threadIdx.x;
+    if (level >= p.nlevels) return;
     const EfLevelCounters* ctr = &p.counters[frame * EF_MAX_LEVELS];
-    int level = p.first_level, offset = 0;
-    while (level + 1 < p.nlevels && row >= offset + ctr[level].selected) { offset += ctr[level].selected; level++; }
-    const EfLevel& L = p.lv[level];
-    const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[row - offset];
-    if ((unsigned)((k.y >> 5) - L.own_ty0) < (unsigned)L.own_rows) return;      // owned: keep
-    uint8_t* d = p.desc + (size_t)frame * p.desc_stride + (size_t)row * p.desc_pitch + 16 * ch;
-    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-    else for (int i = 0; i < 16; i++) d[i] = 0;
+    int lo = 1 << 30, hi = -(1 << 30);                       // empty: no tile intersects
+    if (level >= p.first_level) {
+        int offset = 0;
+        for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
+        const int nsel = min(ctr[level].selected, max(p.nfeatures - offset, 0));
+        const int a = max(p.desc_row0 - offset, 0), b = min(p.desc_row0 + p.desc_rows - offset, nsel);
+        if (a < b) {
+            const EfSelected* sel = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, p.lv[level].sel_off));
+            lo = sel[a].y - 24; hi = sel[b - 1].y + 24;      // the selected list is in raster order
+        }
+    }
+    slice_y[(frame * EF_MAX_LEVELS + level) * 2] = lo;
+    slice_y[(frame * EF_MAX_LEVELS + level) * 2 + 1] = hi;
 }
 
 void ef_launch_band_pack(const EfPipe& p, uint8_t* cand, unsigned long long cand_stride, cudaStream_t s)
@@ -1632,10 +1642,8 @@ void ef_launch_band_merge(const EfPipe& p, const uint8_t* all, unsigned long lon
     ef_band_merge_kernel<<<dim3(p.nlevels, p.nframes), 256, 0, s>>>(p, all, cand_stride, nshards);
     EF_COUNT_LAUNCH(1);
 }
-void ef_launch_band_mask_rows(const EfPipe& p, bool hashsift, cudaStream_t s)
+void ef_launch_band_slice_ranges(const EfPipe& p, int* slice_y, cudaStream_t s)
 {
-    const int threads = p.nfeatures * (p.desc_bytes / 16);
-    (void)hashsift;
-    ef_band_mask_rows_kernel<<<dim3(ef_div_up(threads, 256), p.nframes), 256, 0, s>>>(p);
+    ef_band_slice_ranges_kernel<<<p.nframes, 32, 0, s>>>(p, slice_y);
     EF_COUNT_LAUNCH(1);
 }

@@ -390,14 +390,11 @@ __global__ void __launch_bounds__(EF_SIFT_WARPS * 32) ef_hashsift_pipe_kernel(co
     const int i = (bx - L.sift_block_start) * EF_SIFT_KP_PER_CTA + slot;
     int offset = 0;
     for (int l = p.first_level; l < level; l++) offset += ctr[l].selected;
-    bool valid = i < nsel && offset + i < p.nfeatures;
+    // band-sharded frame: only the output rows of this GPU's slice; a warp whose two keypoints belong to other GPUs leaves
+    const bool valid = i < nsel && offset + i < p.nfeatures && (unsigned)(offset + i - p.desc_row0) < (unsigned)p.desc_rows;
+    if (!__any_sync(0xffffffffu, valid)) return;
     const int ii = valid ? i : first;
     const EfSelected k = reinterpret_cast<const EfSelected*>(ef_ws(p, frame, L.sel_off))[ii];
-    if (p.desc_by_band) {
-        // band-sharded frame: only the keypoints of this GPU's band; a warp whose two keypoints belong to other bands leaves
-        valid = valid && (unsigned)((k.y >> 5) - L.own_ty0) < (unsigned)L.own_rows;
-        if (!__any_sync(0xffffffffu, valid)) return;
-    }
     const uint8_t* __restrict__ img = ef_ws(p, frame, L.blur_off);
     // describer created with croppingScale 1, keypoint size PATCH_SIZE (cuda_efficient_features.cpp:58-62, .cu:260)
     ef_hashsift_one<true, V>(img, L.w, L.h, L.blur_pitch, (float)k.x, (float)k.y, EF_PATCH_SIZE, k.angle, 1.f, t, sm[warp],

@@ -36,7 +36,7 @@ EXPORTS = [
     "ef_stage_timing_enable", "ef_stage_times", "ef_kernel_launch_count",
     "ef_mg_create", "ef_mg_destroy", "ef_mg_device_count", "ef_mg_shard_range", "ef_mg_detect_and_compute_host_batch",
     "ef_mg_last_error_string",
-    "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows",
+    "ef_band_candidate_bytes", "ef_band_detect_async", "ef_band_finish_async", "ef_band_tile_rows", "ef_band_desc_rows",
     "ef_match_scratch_bytes", "ef_match_knn_async", "ef_match_cross_check_async", "ef_match_ratio_cross_async",
     "ef_match_last_error_string", "ef_bgr_to_gray_async", "ef_debug_project_async", "ef_synth_frames_async",
 ]
@@ -117,6 +117,8 @@ def load_library() -> C.CDLL:
     L.ef_band_finish_async.argtypes = [vp, i32, i32, i32, vp, vp, sz, sz, vp, sz, sz, vp, vp]
     L.ef_band_tile_rows.argtypes = [i32, i32, i32, i32] + [C.POINTER(i32)] * 4
     L.ef_band_tile_rows.restype = None
+    L.ef_band_desc_rows.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.ef_band_desc_rows.restype = None
     L.ef_match_scratch_bytes.argtypes = [i32, i32]
     L.ef_match_scratch_bytes.restype = sz
     L.ef_match_knn_async.argtypes = [vp, sz, i32, vp, sz, i32, i32, i32, vp, vp, vp, vp]
@@ -346,7 +348,8 @@ class EfficientFeatures:
 
     def bandFinish(self, all_cand, shard: int, nshards: int, stream=None, want_descriptors=True, out=None):
         """Phase 2: all_cand = nshards x F x bandCandidateBytes() (all-gathered).  Returns (F x 5 x nfeatures keypoints --
-        complete and identical on every GPU --, F x nfeatures x B descriptors with only this GPU's rows non-zero, F counts)."""
+        complete and identical on every GPU --, F x nfeatures x B descriptors of which only this GPU's block of output rows
+        (efb200.tiling.band_desc_rows) is filled, F counts)."""
         torch = _torch()
         if not (isinstance(all_cand, torch.Tensor) and all_cand.is_cuda and all_cand.dtype == torch.uint8 and all_cand.is_contiguous()
                 and all_cand.dim() == 3 and all_cand.shape[0] == nshards and all_cand.shape[2] == self.bandCandidateBytes()):

@@ -3,14 +3,15 @@
 Every rank holds the whole image (rank `src` broadcasts it over NCCL/NVLink -- the only image movement), builds the whole
 pyramid, and runs FAST/Harris + radius NMS + compaction on its band of every level.  Two small collectives complete the
 frame: an all-gather of the per-band top-quota candidates (<= 8 B x nfeatures per rank) before the global per-level
-selection, and an element-wise MAX all-reduce of the descriptor matrix (each rank fills only the rows of its share of the
-keypoints, the others are zero).  The result on every rank is bit-identical to the single-GPU result.
+selection, and an all-gather of the descriptor matrix in equal blocks of output rows (rank g describes rows
+[g C, (g + 1) C), C = ceil(nfeatures / world): 1/world of the bytes per rank, no reduction anywhere).  The result on every rank
+is bit-identical to the single-GPU result.
 """
 from __future__ import annotations
 
 import ctypes as C
 
-COLLECTIVES = "NCCL broadcast of the image, all-gather of band candidates, MAX all-reduce of the descriptor matrix"
+COLLECTIVES = "NCCL broadcast of the image, all-gather of band candidates, all-gather of equal descriptor row blocks (no reduction)"
 
 
 def band_tile_rows(tiles_y: int, shard: int, nshards: int, halo_tiles: int = 1):
@@ -21,6 +22,15 @@ def band_tile_rows(tiles_y: int, shard: int, nshards: int, halo_tiles: int = 1):
     v = [C.c_int() for _ in range(4)]
     L.ef_band_tile_rows(tiles_y, shard, nshards, halo_tiles, *[C.byref(x) for x in v])
     return tuple(x.value for x in v)
+
+
+def band_desc_rows(nfeatures: int, shard: int, nshards: int):
+    """(row0, nrows): the block of descriptor rows `shard` fills (host arithmetic of ef_band_desc_rows; callable without a GPU)."""
+    from . import load_library
+    L = load_library()
+    a, b = C.c_int(), C.c_int()
+    L.ef_band_desc_rows(nfeatures, shard, nshards, C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def detect_and_compute_tiled(ef, images, group=None, src=None, want_descriptors=True, out=None):
@@ -42,13 +52,26 @@ def detect_and_compute_tiled(ef, images, group=None, src=None, want_descriptors=
         all_cand = cand[None]
     kp, desc, counts = ef.bandFinish(all_cand, rank, world, want_descriptors=want_descriptors, out=out)
     if world > 1 and desc is not None:
-        dist.all_reduce(desc, op=dist.ReduceOp.MAX, group=group)
+        # every rank filled rows [rank C, (rank + 1) C) of every frame: all-gather of the equal blocks.  In place when the matrix
+        # holds world * C rows (nfeatures divisible by world); otherwise through a padded buffer.
+        F, nf, B = desc.shape
+        row0, c = band_desc_rows(nf, rank, world)
+        for f in range(F):
+            if world * c == nf and desc[f].is_contiguous():
+                dist.all_gather_into_tensor(desc[f].view(-1), desc[f, row0:row0 + c].reshape(-1), group=group)
+            else:
+                mine = torch.zeros((c, B), dtype=desc.dtype, device=desc.device)
+                n_own = max(0, min(c, nf - row0))
+                mine[:n_own] = desc[f, row0:row0 + n_own]
+                full = torch.empty((world * c, B), dtype=desc.dtype, device=desc.device)
+                dist.all_gather_into_tensor(full.view(-1), mine.view(-1), group=group)
+                desc[f].copy_(full[:nf])
     return kp, desc, counts
 
 
 def detect_and_compute_tiled_emulated(efs, images, want_descriptors=True):
     """The same data flow on ONE GPU with len(efs) handles standing in for the ranks (tests, and a reference for the
-    collective plumbing): concatenation replaces the all-gather, an element-wise maximum the all-reduce."""
+    collective plumbing): concatenation replaces both all-gathers."""
     import torch
     n = len(efs)
     cands = [ef.bandDetect(images, g, n) for g, ef in enumerate(efs)]
@@ -56,6 +79,9 @@ def detect_and_compute_tiled_emulated(efs, images, want_descriptors=True):
     outs = [ef.bandFinish(all_cand, g, n, want_descriptors=want_descriptors) for g, ef in enumerate(efs)]
     kp, desc, counts = outs[0]
     if desc is not None:
-        for o in outs[1:]:
-            desc = torch.maximum(desc, o[1])
+        nf = desc.shape[1]
+        desc = desc.clone()
+        for g, o in enumerate(outs):
+            row0, c = band_desc_rows(nf, g, n)
+            desc[:, row0:row0 + c] = o[1][:, row0:row0 + c]
     return kp, desc, counts, outs

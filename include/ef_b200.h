@@ -150,9 +150,10 @@ const char* ef_mg_last_error_string(const ef_mg_handle* m);
  * d_cand (ef_band_candidate_bytes() per frame).  The caller all-gathers the candidate buffers of all GPUs in shard order
  * ([nshards][nframes][bytes]; <= 8 B x nfeatures per GPU) and calls ef_band_finish_async, which re-selects the global
  * top-quota (bit-identical to the single-GPU result), writes the FULL keypoint matrix on every GPU and the descriptors of
- * this GPU's share of the keypoints (descriptor CTAs dealt round-robin), all other descriptor rows zero: an element-wise
- * MAX all-reduce (uint8) of d_desc assembles the frame's descriptors on every GPU.  nshards == 1 degenerates to
- * ef_detect_and_compute_batch_async.  Replaces the same reference entry (src/cuda_efficient_features.cpp:225-321). */
+ * this GPU's block of output rows [row0, row0 + nrows) (ef_band_desc_rows: equal blocks of ceil(nfeatures / nshards) rows; the other
+ * rows are left undefined): an all-gather of the fixed-size row blocks -- in place over d_desc when its capacity is
+ * nshards * nrows rows -- assembles the frame's descriptors on every GPU.  No reduction crosses the GPUs.  nshards == 1
+ * degenerates to ef_detect_and_compute_batch_async.  Replaces the same reference entry (src/cuda_efficient_features.cpp:225-321). */
 size_t ef_band_candidate_bytes(const ef_handle* h);
 int ef_band_detect_async(ef_handle* h, int shard, int nshards, int nframes, const uint8_t* d_imgs, size_t img_stride, size_t pitch,
                          int width, int height, uint8_t* d_cand, void* stream);
@@ -162,6 +163,7 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
 /* host arithmetic of the band partition: tile rows (32 pixel rows each) of a level with `tiles_y` tile rows owned by `shard`
  * and the rows its score stage covers with `halo_tiles` extra tile rows on either side */
 void ef_band_tile_rows(int tiles_y, int shard, int nshards, int halo_tiles, int* own0, int* own_n, int* score0, int* score_n);
+void ef_band_desc_rows(int nfeatures, int shard, int nshards, int* row0, int* nrows);
 
 /* ---- callers either side of the path ------------------------------------------------------------
  * Brute-force Hamming matcher on the descriptors the path produced (32- or 64-byte rows), stateless.

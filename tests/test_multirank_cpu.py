@@ -80,8 +80,8 @@ def test_band_partition_covers_every_tile_row_once():
 class _StubFeatures:
     """Stands in for EfficientFeatures on CPU tensors: checks what the collectives deliver."""
 
-    def __init__(self, rank, world):
-        self.rank, self.world = rank, world
+    def __init__(self, rank, world, nf=10):
+        self.rank, self.world, self.nf = rank, world, nf
 
     def bandDetect(self, images, shard, nshards, stream=None):
         import torch
@@ -93,9 +93,11 @@ class _StubFeatures:
         assert tuple(all_cand.shape) == (nshards, 2, 48)
         for g in range(nshards):   # shard order, every rank's candidates
             assert int(all_cand[g, 0, 0]) == g + 1 + 7
-        desc = torch.zeros((2, 10, 4), dtype=torch.uint8)
-        desc[:, shard::nshards] = 100 + shard
-        return torch.zeros((2, 5, 10)), desc, torch.full((2,), 10, dtype=torch.int32)
+        from efb200.tiling import band_desc_rows
+        desc = torch.full((2, self.nf, 4), 255, dtype=torch.uint8)        # rows of other ranks: undefined (here 255)
+        row0, c = band_desc_rows(self.nf, shard, nshards)
+        desc[:, row0:row0 + c] = 100 + shard
+        return torch.zeros((2, 5, self.nf)), desc, torch.full((2,), self.nf, dtype=torch.int32)
 
 
 def _band_worker(rank, world, port, q):
@@ -107,8 +109,9 @@ def _band_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     images = torch.full((2, 64, 64), 7 if rank == 0 else 0, dtype=torch.uint8)   # only the source rank has the frame
-    kp, desc, counts = detect_and_compute_tiled(_StubFeatures(rank, world), images, src=0)
-    q.put((rank, desc[0, :, 0].tolist(), int(images[1, 5, 5])))
+    kp, desc, counts = detect_and_compute_tiled(_StubFeatures(rank, world, 10), images, src=0)
+    kp, desc_odd, counts = detect_and_compute_tiled(_StubFeatures(rank, world, 7), images, src=0)   # 7 rows: not divisible, padded path
+    q.put((rank, desc[0, :, 0].tolist() + desc_odd[1, :, 3].tolist(), int(images[1, 5, 5])))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -126,4 +129,4 @@ def test_band_collectives_gloo():
         assert p.exitcode == 0
     for rank, rows, px in res:
         assert px == 7                                      # image broadcast from rank 0
-        assert rows == [100, 101] * 5                       # MAX all-reduce assembled the rows of both ranks
+        assert rows == [100] * 5 + [101] * 5 + [100] * 4 + [101] * 3   # all-gather of the equal row blocks (in place / padded)

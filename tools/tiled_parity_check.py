@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""torchrun script: band-sharded detectAndCompute over real NCCL (broadcast + all-gather + MAX all-reduce) must equal the
+"""torchrun script: band-sharded detectAndCompute over real NCCL (broadcast + all-gather of candidates + all-gather of descriptor row blocks) must equal the
 single-GPU result on every rank, bit for bit.  Prints one line per rank; exit code != 0 on mismatch."""
 import os
 import sys
@@ -20,7 +20,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (w, h, nf, dt) in [(3840, 2160, 40000, efb200.HASH_SIFT_512), (1920, 1080, 5000, efb200.BAD_256), (7680, 4320, 40000, efb200.BAD_512)]:
+    for (w, h, nf, dt) in [(3840, 2160, 40000, efb200.HASH_SIFT_512), (1920, 1080, 5000, efb200.BAD_256), (7680, 4320, 40000, efb200.BAD_512), (1280, 720, 3001, efb200.HASH_SIFT_256)]:
         g = torch.Generator(device="cpu").manual_seed(1234 + w)
         img = torch.randint(0, 256, (1, h, w), dtype=torch.uint8, generator=g)
         d = img.cuda() if rank == 0 else torch.zeros_like(img).cuda()
