@@ -138,6 +138,7 @@ struct ef_handle {
     uint4* d_hs_bfrag[2] = { nullptr, nullptr };     // fixed-point digits of the projection in mma fragment order (ef_project.cu)
     long long* d_hs_bias[2] = { nullptr, nullptr };  // column 0 of the projection as fixed-point integers
     int hs_shift[2] = { 0, 0 };                      // fixed-point scale 2^-shift; bfrag == nullptr: table does not fit 6 digits
+    int hs_ndig[2] = { 0, 0 };                       // digits per weight in d_hs_btc (6 or 7); 0: no integer form (fp64 kernel)
     float* d_exp_table = nullptr;
     float2* d_grad_table = nullptr;
 
@@ -165,7 +166,7 @@ struct ef_handle {
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_blur = false;  // measured: +0.3 % (5.181 vs 5.195 ms per 8 frames) -- the blur saturates the GPU by itself, the short kernels only queue behind it
-    int host_chunk = 4;
+    int host_chunk = 0;         // frames per chunk of the host-buffer pipeline; 0 = geometric plan 1, 2, 4, ... (measured: 10.43 vs 10.52 ms per 16 frames for chunks of 4)
 
     // optional per-stage timing (bench.py): events recorded between the stages
     bool timing = false;
@@ -339,24 +340,30 @@ int upload_tables(ef_handle* h)
                 W[i] = (long long)scaled;
                 if ((double)W[i] != scaled) ok = false;
             }
+            // six balanced base-256 digits when they suffice (512-bit table: 47-bit integers), seven otherwise (256-bit table: 49 bits)
             std::vector<signed char> dig; std::vector<long long> bias(nbits);
-            if (ok) {
-                dig.assign((size_t)6 * nbits * 128, 0);
-                for (int j = 0; ok && j < nbits; j++) {
+            int ndig = 0;
+            for (int nd = 6; ok && nd <= 7 && !ndig; nd++) {
+                bool fits = true;
+                dig.assign((size_t)nd * nbits * 128, 0);
+                for (int j = 0; fits && j < nbits; j++) {
                     bias[j] = W[(size_t)j * 129];
                     for (int k = 0; k < 128; k++) {
                         long long x = W[(size_t)j * 129 + 1 + k];
-                        for (int d = 0; d < 6; d++) {
+                        for (int d = 0; d < nd; d++) {
                             const long long r = ((x + 128) & 255) - 128;     // balanced digit in [-128, 127]
                             dig[((size_t)d * nbits + j) * 128 + k] = (signed char)r;
                             x = (x - r) / 256;
                         }
-                        if (x != 0) ok = false;
+                        if (x != 0) { fits = false; break; }
                     }
-                    if (std::llabs(bias[j]) >= (1ll << 61)) ok = false;
+                    if (std::llabs(bias[j]) >= (1ll << 61)) fits = false;
                 }
+                if (fits) ndig = nd;
             }
-            if (ok) {
+            ok = ok && ndig != 0;
+            h->hs_ndig[v] = ok ? ndig : 0;
+            if (ok && ndig == 6) {
                 // fragment order: bfrag[ntile][digit][half][lane] = { b0(ks=2*half), b1(ks=2*half), b0(ks=2*half+1), b1(ks=2*half+1) }
                 // with b0 = digits of output bit 8*ntile + lane/4 at k = 32*ks + 4*(lane%4) .. +3 and b1 the same at k + 16
                 const int ntiles = nbits / 8;
@@ -372,18 +379,20 @@ int upload_tables(ef_handle* h)
                                 o[2] = word(d, j, 32 * (2 * half + 1) + kq); o[3] = word(d, j, 32 * (2 * half + 1) + kq + 16);
                             }
                 EF_CUDA(h, cudaMalloc(&h->d_hs_bfrag[v], frag.size() * sizeof(unsigned int)));
-                EF_CUDA(h, cudaMalloc(&h->d_hs_bias[v], bias.size() * sizeof(long long)));
                 EF_CUDA(h, cudaMemcpy(h->d_hs_bfrag[v], frag.data(), frag.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+            }
+            if (ok) {
+                EF_CUDA(h, cudaMalloc(&h->d_hs_bias[v], bias.size() * sizeof(long long)));
                 EF_CUDA(h, cudaMemcpy(h->d_hs_bias[v], bias.data(), bias.size() * sizeof(long long), cudaMemcpyHostToDevice));
                 h->hs_shift[v] = S;
                 // tcgen05 operand order: btc[chunk of 32 output bits][digit][4 KB], inside a 4 KB block the UMMA no-swizzle K-major
                 // core-matrix layout: (n / 8) * 1024 + (k / 16) * 128 + (n % 8) * 16 + (k % 16)
-                std::vector<signed char> btc((size_t)6 * nbits * 128);
+                std::vector<signed char> btc((size_t)ndig * nbits * 128);
                 for (int j = 0; j < nbits; j++)
-                    for (int d = 0; d < 6; d++)
+                    for (int d = 0; d < ndig; d++)
                         for (int k = 0; k < 128; k++) {
                             const int c = j / 32, nl = j % 32;
-                            btc[((size_t)c * 6 + d) * 4096 + (nl / 8) * 1024 + (k / 16) * 128 + (nl % 8) * 16 + (k % 16)] = dig[((size_t)d * nbits + j) * 128 + k];
+                            btc[((size_t)c * ndig + d) * 4096 + (nl / 8) * 1024 + (k / 16) * 128 + (nl % 8) * 16 + (k % 16)] = dig[((size_t)d * nbits + j) * 128 + k];
                         }
                 EF_CUDA(h, cudaMalloc(&h->d_hs_btc[v], btc.size()));
                 EF_CUDA(h, cudaMemcpy(h->d_hs_btc[v], btc.data(), btc.size(), cudaMemcpyHostToDevice));
@@ -476,7 +485,7 @@ int allocate(ef_handle* h)
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     if (const char* e = std::getenv("EF_B200_OVERLAP_BLUR")) h->overlap_blur = std::atoi(e) != 0;   // 1: blur on the side stream (A/B switch)
-    if (const char* e = std::getenv("EF_B200_HOST_CHUNK")) h->host_chunk = std::max(1, std::atoi(e)); // frames per pipeline chunk of the host API
+    if (const char* e = std::getenv("EF_B200_HOST_CHUNK")) h->host_chunk = std::max(0, std::atoi(e)); // frames per pipeline chunk of the host API (0: geometric plan)
     h->ev_in.resize(p.max_batch); h->ev_cnt.resize(p.max_batch);
     for (int i = 0; i < p.max_batch; i++) {
         EF_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
@@ -627,7 +636,7 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
             EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
-            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v], h->hs_ndig[v] };
             ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, P.desc_bytes * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, h->keep_proj ? h->d_proj : nullptr, s);
             mark(h, EF_STAGE_PROJECT, s);
@@ -798,7 +807,7 @@ static int compute_common(ef_handle* h, const uint8_t* d_img, size_t pitch, int 
     } else {
         EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
         ef_launch_hashsift_features_flat(job, t, h->d_sift128, s);
-        const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
+        const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v], h->hs_ndig[v] };
         ef_launch_hashsift_project_batch(h->d_sift128, n, nullptr, 1, pt, job.nbits, d_desc, 0, (int)desc_pitch,
                                          h->keep_proj ? h->d_proj : nullptr, s);
     }
@@ -851,14 +860,24 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     // download of chunk c-1 (:316-320) overlap the kernels of chunk c.  Chunks reuse workspace slots [0, chunk): their
     // kernels are serialised on the caller's stream; outputs land in per-frame staging buffers.
     // chunk plan: a ONE-frame head chunk (the kernels start after 8 MB instead of a whole chunk of uploads), host_chunk frames each,
-    const int chunk = std::max(1, std::min(h->host_chunk, nframes));
     std::vector<std::pair<int, int>> plan;   // (first frame, frames)
-    // and a ONE-frame tail chunk (only 2.5 MB of results are still to be downloaded when the last kernel ends)
-    const bool ends = nframes > chunk + 1 && chunk > 1;
-    if (ends) plan.emplace_back(0, 1);
-    const int body_end = ends ? nframes - 1 : nframes;
-    for (int f = ends ? 1 : 0; f < body_end; f += chunk) plan.emplace_back(f, std::min(chunk, body_end - f));
-    if (ends) plan.emplace_back(nframes - 1, 1);
+    if (h->host_chunk <= 0) {
+        // geometric plan (EF_B200_HOST_CHUNK=0): 1, 2, 4, 8, ... frames -- the kernels start after ONE frame is up, every later chunk is
+        // uploaded while the previous (half as large) one computes, launches per frame fall -- and a one-frame tail, so that only
+        // 2.5 MB of results are still to be downloaded when the last kernel ends
+        const bool tail = nframes >= 4;
+        const int body_end = tail ? nframes - 1 : nframes;
+        for (int f = 0, c = 1; f < body_end; f += c, c *= 2) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
+        if (tail) plan.emplace_back(nframes - 1, 1);
+    } else {
+        const int chunk = std::max(1, std::min(h->host_chunk, nframes));
+        // and a ONE-frame tail chunk (only 2.5 MB of results are still to be downloaded when the last kernel ends)
+        const bool ends = nframes > chunk + 1 && chunk > 1;
+        if (ends) plan.emplace_back(0, 1);
+        const int body_end = ends ? nframes - 1 : nframes;
+        for (int f = ends ? 1 : 0; f < body_end; f += chunk) plan.emplace_back(f, std::min(chunk, body_end - f));
+        if (ends) plan.emplace_back(nframes - 1, 1);
+    }
     const int nchunks = (int)plan.size();
     if ((int)h->ev_in.size() < nchunks || (int)h->ev_cnt.size() < nchunks) return fail(h, EF_ERR_CAPACITY, "internal: chunk events");
     EF_CUDA(h, cudaEventRecord(h->ev_in[0], s));          // order the uploads after earlier work on the caller's stream
@@ -993,7 +1012,7 @@ int ef_band_finish_async(ef_handle* h, int shard, int nshards, int nframes, cons
             ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
             // the projection runs over all rows: rows of other GPUs come out of stale SIFT vectors and are overwritten by the all-gather
-            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
+            const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v], h->hs_ndig[v] };
             ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, db * 8,
                                              P.desc, (size_t)P.desc_stride, P.desc_pitch, nullptr, s);
             mark(h, EF_STAGE_PROJECT, s);
@@ -1050,7 +1069,7 @@ int ef_debug_project_async(ef_handle* h, const uint8_t* d_sift128, int n, int pa
     if (n == 0) return EF_OK;
     EF_ON_DEVICE(h);
     const int db = desc_bytes_of(h->prm.desc_type), v = db == 32 ? 0 : 1;
-    const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v] };
+    const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v], h->hs_ndig[v] };
     g_ef_project_path = path;   // tests only: not thread safe
     ef_launch_hashsift_project_batch(d_sift128, n, nullptr, 1, pt, db * 8, d_desc, 0, (int)desc_pitch, nullptr, (cudaStream_t)stream);
     g_ef_project_path = 0;

@@ -202,7 +202,8 @@ void ef_launch_hashsift_features_pipe(const EfPipe& p, const EfHashSiftTables& t
 // projection + sign + pack.  rows = keypoint rows in sift128 (n x 128 u8).  bfrag != nullptr: exact integer-tensor-core
 // path (fixed-point digits of the weights in mma fragment order, int64 bias, scale 2^-shift); else fp64 fallback on weights_t.
 struct EfProjTables { const uint4* bfrag; const long long* bias; int shift; const float* weights_t; /*129 x nbits*/
-                      const uint8_t* btc; /* digits in UMMA core-matrix order for the tcgen05 path (ef_project_tc.cu), or nullptr */ };
+                      const uint8_t* btc; /* digits in UMMA core-matrix order for the tcgen05 path (ef_project_tc.cu), or nullptr */
+                      int ndigits;        /* balanced base-256 digits per weight in btc: 6 (512-bit table) or 7 (256-bit table) */ };
 bool ef_launch_hashsift_project_tc(const uint8_t* sift128, int n_cap, const int* d_counts, int nframes, const EfProjTables& t, int nbits,
                                    uint8_t* desc, size_t desc_stride, int desc_pitch, float* proj_out, cudaStream_t s);
 extern int g_ef_project_path;
