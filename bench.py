@@ -360,9 +360,13 @@ def main():
             from efb200 import tiling
             fr2 = efb200.synth_frames(2, 4320, 7680, SEED, first_frame=100000, device=dev)
             out2 = (kp[:2], desc[:2], counts[:2])
+            ef8.stageTimingEnable(True)
             t5 = timed(lambda: tiling.detect_and_compute_tiled(ef8, fr2, src=0, out=out2), 5)
+            st8, _ = ef8.stageTimes()            # kernels of this rank (warm-up steps included: 7 steps); the rest of a step is collectives + gaps
+            ef8.stageTimingEnable(False)
             extras["oversized frame: 2 x 8K HASH_SIFT_512 cut into bands"] = {
                 "ms_per_step": t5, "frames_per_step": 2, "Mpix_per_s": 2 * 7680 * 4320 / (t5 * 1e-3) / 1e6, "bands": world, "scaling": "strong",
+                "single_gpu_ms_per_step": t3 * 2 / B8, "rank0_kernel_ms_per_step": {k: round(v / 7, 4) for k, v in st8.items() if v > 0},
                 "collectives": tiling.COLLECTIVES}
             del fr2
         del ef8, frames8
