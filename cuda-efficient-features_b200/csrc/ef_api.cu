@@ -861,13 +861,23 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
     // kernels are serialised on the caller's stream; outputs land in per-frame staging buffers.
     // chunk plan: a ONE-frame head chunk (the kernels start after 8 MB instead of a whole chunk of uploads), host_chunk frames each,
     std::vector<std::pair<int, int>> plan;   // (first frame, frames)
-    if (h->host_chunk <= 0) {
-        // geometric plan (EF_B200_HOST_CHUNK=0): 1, 2, 4, 8, ... frames -- the kernels start after ONE frame is up, every later chunk is
+    if (const char* e = std::getenv("EF_B200_HOST_PLAN")) {
+        // explicit chunk sizes for experiments, e.g. "2,4,8,2" (the last size repeats until the batch is covered)
+        int f = 0, c = 1;
+        const char* q = e;
+        while (f < nframes) {
+            if (*q) { c = std::max(1, std::atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+            c = std::min(c, nframes - f);
+            plan.emplace_back(f, c); f += c;
+        }
+    } else if (h->host_chunk <= 0) {
+        // geometric plan (EF_B200_HOST_CHUNK=0): 1, 2, 4, 8, 16, 16, ... frames -- the kernels start after ONE frame is up, every later chunk is
         // uploaded while the previous (half as large) one computes, launches per frame fall -- and a one-frame tail, so that only
         // 2.5 MB of results are still to be downloaded when the last kernel ends
         const bool tail = nframes >= 4;
         const int body_end = tail ? nframes - 1 : nframes;
-        for (int f = 0, c = 1; f < body_end; f += c, c *= 2) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
+        const int cap = 16;  // larger chunks only lengthen the download that is still pending when the last kernel ends
+        for (int f = 0, c = 1; f < body_end; f += c, c = std::min(2 * c, cap)) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
         if (tail) plan.emplace_back(nframes - 1, 1);
     } else {
         const int chunk = std::max(1, std::min(h->host_chunk, nframes));
