@@ -5,7 +5,7 @@
 // Compiled with -fmad=false: the CPU reference is a generic x86-64 build without FMA, so every a*b+c below
 // stays two roundings.
 //
-// One HALF-WARP per keypoint (2 keypoints per warp, 4 per 64-thread CTA, ~9.5 KB of shared memory each):
+// One HALF-WARP per keypoint (2 keypoints per warp, 4 per 64-thread CTA, 7.9 KB of shared memory each -- seven CTAs per SM):
 //   1. (detectAndCompute path) the 48x48-pixel window that bounds the rotated patch is staged in shared memory
 //      with aligned 32-bit loads; the 32x32 bilinear samples (hash_sift.cpp:88-106) then read bytes from it.
 //   2. per gradient pixel (30x30): dx,dy in [-255,255] index ONE 8-byte table entry holding sqrtf(dx^2+dy^2),
@@ -31,25 +31,31 @@
 #define EF_SIFT_KP_PER_CTA (2 * EF_SIFT_WARPS)
 #define EF_SIFT_REC 916                 // floats per record array (30x30 skewed needs 906)
 #define EF_SIFT_ZERO 908                // spare record slot (skewed 30x30 indices end at 905) holding an all-zero record
-#define EF_SIFT_BLK (2 * EF_SIFT_REC)   // record block of one keypoint (16-byte multiple): magnitudes then fractions
-#define EF_SIFT_WIN 48                  // staged window edge (pixels); every sample of a size-31 patch lies in [k-22, k+22]
+#define EF_SIFT_BLK 1872                // floats per keypoint block (16-byte multiple): magnitudes, fractions, slack
+#define EF_SIFT_WIN_ROWS 46             // staged window rows k-22 .. k+23: every sample of a size-31 patch lies in [k-22, k+22]
+#define EF_SIFT_WIN 48                  // staged window columns start at (k - 24) & ~15
 #define EF_SIFT_WIN_PITCH 136           // bytes per staged row: 64 pixels (48 + up to 15 alignment bytes), TWO bytes each -- entry x holds
                                         // (pixel x, pixel x+1), so a bilinear sample is two 16-bit loads; 34-word pitch spreads the banks
+#define EF_SIFT_PATCH_OFF 6464          // byte offset of the 32x32 u8 patch inside the keypoint block
+#define EF_SIFT_GB 8                    // gradient pixels per lane and step (gathers in flight; 16: +0.3 %, measured)
 
-struct EfSiftWarpSmem {                 // per warp = 2 keypoints
+// Shared memory of one warp = 2 keypoints: 16 128 bytes, so that SEVEN 2-warp CTAs fit one SM (2 x 16128 + 1024 reserved = 33280 = 130 x 256-byte allocation units, 7 x 33280 <= 233472;
+// 18.9 KB per warp gave six).  One block per keypoint is used three times over:
+//   staging   bytes [0, 46 x 136) the 46 x 64 window, while the sampler writes the patch at [PATCH_OFF, PATCH_OFF + 1024)
+//   gradients magnitude[i] at float k + i (sign bit = bin bit 2), fraction[i] at float REC + k + i (bits 31:30 = bin bits 1:0), written
+//             in steps of 128 pixels while the patch is still being read: the fraction records of pixel i >= 704 land ON the patch, at
+//             patch byte 4 (i + k + 916) - PATCH_OFF, always in rows that no later step reads (tests/test_layout_hashsift.py replays the
+//             schedule); inside a step every lane reads before any lane writes (__syncwarp)
+//   histogram records read only; afterwards the first 128 floats hold the descriptor being normalised
+// The "+ k" puts the records of the second keypoint on the other bank parity (block stride = 1872 words, even).
+struct EfSiftWarpSmem {
     float hist[9 * 32];                 // [bin 0..8][lane]
-    // the two patches lie 16736 bytes apart = 24 banks (mod 32): the 16-byte runs the two half-warps touch in the same instruction
-    // (sample stores, gradient neighbour loads) fall on different banks
-    uint8_t patch0[32 * 32];
-    // per keypoint k: magnitude[i] (sign bit = bin bit 2) at rec[k][k + i], fraction[i] (bits 31:30 = bin bits 1:0) at
-    // rec[k][REC + k + i]: the "+ k" puts the second keypoint on the other bank parity.  Phase 1 aliases the staging window here.
-    __align__(16) float rec[2][EF_SIFT_BLK + 4];
-    float desc[2][128];
-    uint8_t patch1[32 * 32];
+    __align__(16) float blk[2][EF_SIFT_BLK];
 };
-static_assert(sizeof(EfSiftWarpSmem) == 18912, "6 CTAs of 2 warps per SM need <= 18912 bytes per warp");
-static_assert(EF_SIFT_WIN * EF_SIFT_WIN_PITCH <= EF_SIFT_BLK * 4, "staging window must fit the record block it aliases");
-static_assert((EF_SIFT_BLK + 4) % 4 == 0, "record blocks must stay 16-byte aligned");
+static_assert(sizeof(EfSiftWarpSmem) == 16128 && 7 * (EF_SIFT_WARPS * sizeof(EfSiftWarpSmem) + 1024) <= 233472 && (EF_SIFT_WARPS * sizeof(EfSiftWarpSmem) + 1024) % 256 == 0, "7 CTAs of 2 warps per SM");
+static_assert(EF_SIFT_WIN_ROWS * EF_SIFT_WIN_PITCH <= EF_SIFT_PATCH_OFF, "the staged window must end below the patch");
+static_assert(EF_SIFT_PATCH_OFF % 16 == 0 && EF_SIFT_PATCH_OFF + 1024 <= EF_SIFT_BLK * 4, "patch inside the block");
+static_assert(4 * (2 * EF_SIFT_REC + 1) <= EF_SIFT_BLK * 4 && EF_SIFT_BLK % 4 == 0, "both record arrays inside the block");
 
 // normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
 __device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
@@ -76,7 +82,8 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                                                 const EfHashSiftTables& t, EfSiftWarpSmem& sm, uint8_t* out128, bool store)
 {
     const int lane = threadIdx.x & 31, hl = lane & 15, k = lane >> 4;
-    uint8_t* __restrict__ patch = k ? sm.patch1 : sm.patch0;
+    float* __restrict__ blk = sm.blk[k];
+    uint8_t* __restrict__ patch = reinterpret_cast<uint8_t*>(blk) + EF_SIFT_PATCH_OFF;
     // ---- rectifyPatch + warpAffineLinear (hash_sift.cpp:68-138)
     {
         const float PI_1_0F = 3.14159274f;
@@ -90,24 +97,26 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
         const uint8_t* __restrict__ base = img;
         int bpitch = pitch, ox = 0, oy = 0;
         if (STAGED) {
-            // 48 rows x 64 pixels (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy; stored as
+            // 46 rows x 64 pixels (16-byte aligned start <= wx0), four 16-byte loads per row, all 16 lanes busy; stored as
             // overlapping pixel pairs (x, x+1): the first pixel of the next chunk comes from the neighbouring lane
-            const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - EF_SIFT_WIN / 2;
+            const int wx0 = (int)kx - EF_SIFT_WIN / 2, wy0 = (int)ky - (EF_SIFT_WIN_ROWS / 2 - 1);
             const int gx0 = wx0 & ~15;
-            uint8_t* __restrict__ win = reinterpret_cast<uint8_t*>(sm.rec[k]);
+            uint8_t* __restrict__ win = reinterpret_cast<uint8_t*>(blk);
             const int gxc = gx0 + 16 * (hl & 3);
             const bool colok = gxc >= 0 && gxc + 15 < pitch;
 #pragma unroll
-            for (int it = 0; it < EF_SIFT_WIN / 4; it++) {
+            for (int it = 0; it < (EF_SIFT_WIN_ROWS + 3) / 4; it++) {
                 const int row = 4 * it + (hl >> 2), gy = wy0 + row;
                 uint4 v = make_uint4(0, 0, 0, 0);
-                if (colok && gy >= 0 && gy < h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
+                if (colok && gy >= 0 && gy < h && row < EF_SIFT_WIN_ROWS) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gxc));
                 const unsigned nx = __shfl_down_sync(0xffffffffu, v.x, 1); // chunk 3: pixel 64 is never sampled
-                uint2* dst = reinterpret_cast<uint2*>(win + row * EF_SIFT_WIN_PITCH + 32 * (hl & 3));
-                dst[0] = make_uint2(__byte_perm(v.x, 0, 0x2110), __byte_perm(v.x, v.y, 0x4332));
-                dst[1] = make_uint2(__byte_perm(v.y, 0, 0x2110), __byte_perm(v.y, v.z, 0x4332));
-                dst[2] = make_uint2(__byte_perm(v.z, 0, 0x2110), __byte_perm(v.z, v.w, 0x4332));
-                dst[3] = make_uint2(__byte_perm(v.w, 0, 0x2110), __byte_perm(v.w, nx, 0x4332));
+                if (row < EF_SIFT_WIN_ROWS) {
+                    uint2* dst = reinterpret_cast<uint2*>(win + row * EF_SIFT_WIN_PITCH + 32 * (hl & 3));
+                    dst[0] = make_uint2(__byte_perm(v.x, 0, 0x2110), __byte_perm(v.x, v.y, 0x4332));
+                    dst[1] = make_uint2(__byte_perm(v.y, 0, 0x2110), __byte_perm(v.y, v.z, 0x4332));
+                    dst[2] = make_uint2(__byte_perm(v.z, 0, 0x2110), __byte_perm(v.z, v.w, 0x4332));
+                    dst[3] = make_uint2(__byte_perm(v.w, 0, 0x2110), __byte_perm(v.w, nx, 0x4332));
+                }
             }
             __syncwarp();
             base = win; bpitch = EF_SIFT_WIN_PITCH; ox = gx0; oy = wy0;
@@ -194,10 +203,11 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     //      Eight pixels per lane and step, in three explicit stages (patch reads, table gathers, record writes) so that the
     //      eight gathers are in flight together instead of one global round trip per pixel.
     {
-        float* __restrict__ magp = sm.rec[k] + k;
-        float* __restrict__ ofp = sm.rec[k] + EF_SIFT_REC + k;
-        constexpr int GB = 8;   // gathers in flight per lane (16: +0.3 %, measured)
-        for (int i0 = hl; i0 < 900; i0 += 16 * GB) {
+        float* __restrict__ magp = blk + k;
+        float* __restrict__ ofp = blk + EF_SIFT_REC + k;
+        constexpr int GB = EF_SIFT_GB;
+        for (int s0 = 0; s0 < 900; s0 += 16 * GB) {         // warp-uniform trip count: the __syncwarp below is reached by all lanes
+            const int i0 = s0 + hl;
             int tix[GB], rix[GB], pix[GB];
 #pragma unroll
             for (int u = 0; u < GB; u++) {
@@ -214,21 +224,23 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
             float ew[GB];
 #pragma unroll
             for (int u = 0; u < GB; u++) { e[u] = __ldg(t.grad_table + tix[u]); ew[u] = __ldg(t.exp_table + pix[u]); }
+            __syncwarp();                                       // late fraction records overwrite patch rows this step has just read
 #pragma unroll
             for (int u = 0; u < GB; u++) {
                 if (i0 + 16 * u < 900) { magp[rix[u]] = ew[u] * e[u].x; ofp[rix[u]] = e[u].y; }
             }
         }
     }
+    __syncwarp();
     for (int b = 0; b < 9; b++) sm.hist[b * 32 + lane] = 0.f;
     // all-zero record (magnitude +0, fraction 0, bin 0) in a spare slot: what the out-of-patch visits of the border cells read
-    if (hl == 0) { sm.rec[k][k + EF_SIFT_ZERO] = 0.f; sm.rec[k][EF_SIFT_REC + k + EF_SIFT_ZERO] = 0.f; }
+    if (hl == 0) { blk[k + EF_SIFT_ZERO] = 0.f; blk[EF_SIFT_REC + k + EF_SIFT_ZERO] = 0.f; }
     __syncwarp();
     // ---- trilinear histogram (hash_sift.cpp:233-290); cell (rb, cb) in 1..4
     {
         const int rb = (hl >> 2) + 1, cb = (hl & 3) + 1;
-        const float* __restrict__ mp = sm.rec[k] + k;
-        const unsigned* __restrict__ op = reinterpret_cast<const unsigned*>(sm.rec[k] + EF_SIFT_REC + k);
+        const float* __restrict__ mp = blk + k;
+        const unsigned* __restrict__ op = reinterpret_cast<const unsigned*>(blk + EF_SIFT_REC + k);
         float* __restrict__ hc = sm.hist + lane;
         const int xb = 8 * (cb - 2) + 3;
         const float nzh = __uint_as_float(0x80000000u | (blockDim.z - 1u));   // -0.0f at run time, opaque to the compiler
@@ -321,15 +333,17 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 }
             }
         }
-        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: the bin number is <= 7)
-        float* d = sm.desc[k] + hl * 8;
+        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: the bin number is <= 7); the descriptor takes
+        // the place of the first records once every lane is done with them
+        __syncwarp();
+        float* d = blk + hl * 8;
         d[0] = hc[0] + hc[8 * 32];
 #pragma unroll
         for (int b = 1; b < 8; b++) d[b] = hc[b * 32];
     }
     __syncwarp();
     // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
-    float* desc = sm.desc[k];
+    float* desc = blk;
     ef_sift_normalize(desc, hl);
     for (int i = hl; i < 128; i += 16) desc[i] = fminf(desc[i], 0.2f);
     __syncwarp();
