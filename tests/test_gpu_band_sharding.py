@@ -10,7 +10,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 
-def _run(torch, oracle, w, h, nfeat, dtype_name, nshards, frames=1, **kw):
+def _run(torch, oracle, w, h, nfeat, dtype_name, nshards, frames=1, allow_empty=False, **kw):
     import efb200
     from efb200 import tiling
     dt = getattr(efb200, dtype_name)
@@ -26,7 +26,7 @@ def _run(torch, oracle, w, h, nfeat, dtype_name, nshards, frames=1, **kw):
     assert np.array_equal(cnt.cpu().numpy(), cnt0.cpu().numpy())
     for f in range(frames):
         n = int(cnt0[f])
-        assert n > 0
+        assert n > 0 or allow_empty
         for g, o in enumerate(outs):   # the keypoint matrix is complete and identical on every band owner
             assert np.array_equal(o[0][f, :, :n].cpu().numpy().view(np.uint32), kp0[f, :, :n].cpu().numpy().view(np.uint32)), f"keypoints differ on shard {g}"
             assert np.array_equal(efs[g].debugLevelCounts(f), counts0[f]), f"per-level counts differ on shard {g}"
@@ -72,3 +72,23 @@ def test_band_sharded_tiny_nfeatures(oracle, nfeat, nlevels):
     prefix of the quotas and must hold their sum (the buffer is sized from it, not from nfeatures)"""
     import torch
     _run(torch, oracle, 1280, 720, nfeat, "BAD_256", 3, nlevels=nlevels)
+
+
+import os
+
+N_BAND_FUZZ = int(os.environ.get("EF_FUZZ_BAND_CASES", "12"))
+
+
+@pytest.mark.parametrize("case", range(N_BAND_FUZZ))
+def test_band_sharded_random_configuration(oracle, case):
+    """seeded random frame size, pyramid shape, FAST threshold, NMS radius, keypoint budget, descriptor and band count"""
+    import torch
+    rng = np.random.default_rng(0xEFB2B000 + case)
+    w, h = int(rng.integers(120, 1100)), int(rng.integers(120, 800))
+    sf = float(rng.choice([1.1, 1.2, 1.41, 2.0]))
+    nlevels = int(rng.integers(1, 10))
+    while nlevels > 1 and min(w, h) / sf ** (nlevels - 1) < 40.0:
+        nlevels -= 1
+    _run(torch, oracle, w, h, int(rng.choice([3, 50, 700, 2500])), str(rng.choice(["BAD_256", "BAD_512", "HASH_SIFT_256", "HASH_SIFT_512"])),
+         int(rng.integers(2, 9)), frames=int(rng.choice([1, 1, 2])), allow_empty=True, scaleFactor=sf, nlevels=nlevels,
+         fastThreshold=int(rng.choice([5, 20, 50])), nonmaxRadius=int(rng.choice([0, 2, 7, 15, 16, 33, 64])))
