@@ -136,6 +136,13 @@ __device__ __forceinline__ unsigned long long ef_add2(unsigned long long a, unsi
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// round toward -infinity: x + 12582912.f (1.5 * 2^23, ulp 1) = 12582912 + floor(x) for |x| < 2^22 -- floor() on the FMA pipe
+__device__ __forceinline__ unsigned long long ef_add2_rm(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ unsigned long long ef_sub2(unsigned long long a, unsigned long long b)
 {
     unsigned long long r;

@@ -168,31 +168,40 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
             const unsigned long long m02 = ef_pack2(M02, M02), m12 = ef_pack2(M12, M12), one2 = ef_pack2(1.f, 1.f), half2 = ef_pack2(0.5f, 0.5f);
             const float nz = __uint_as_float(0x80000000u | (blockDim.z - 1u));   // -0.0f at run time (blockDim.z == 1), opaque to the compiler
             const unsigned long long nz2 = ef_pack2(nz, nz);
+            // No conversion instruction in the loop (F2I / I2F run on the quarter-rate XU pipe, and ten of them per row made this phase
+            // XU-bound): floor(x) = (x + 1.5 * 2^23, rounded toward -infinity) - 1.5 * 2^23 -- exact for |x| < 2^22, the integer sits in
+            // the low mantissa bits -- and byte -> float by planting the byte in the mantissa of 2^23 (PRMT) and subtracting 2^23.
+            const unsigned long long fl2 = ef_pack2(12582912.f, 12582912.f), m23 = ef_pack2(8388608.f, 8388608.f);
+            const int cu = 0x4B400000 + ox, cv = 0x4B400000 + oy;
 #pragma unroll 4
             for (int y = 0; y < 32; y++) {
                 const float ru = M01 * (float)y, rv = M11 * (float)y;
                 const unsigned long long u2 = ef_add2(ef_add2(cx2, ef_pack2(ru, ru)), m02);
                 const unsigned long long v2 = ef_add2(ef_add2(cy2, ef_pack2(rv, rv)), m12);
-                float ua, ub, va, vb;
-                ef_unpack2(u2, ua, ub); ef_unpack2(v2, va, vb);
-                const int uia = (int)floorf(ua), uib = (int)floorf(ub), via = (int)floorf(va), vib = (int)floorf(vb);
-                const unsigned long long du2 = ef_sub2(u2, ef_pack2((float)uia, (float)uib)), dv2 = ef_sub2(v2, ef_pack2((float)via, (float)vib));
+                const unsigned long long tu2 = ef_add2_rm(u2, fl2), tv2 = ef_add2_rm(v2, fl2);
+                const unsigned long long du2 = ef_sub2(u2, ef_sub2(tu2, fl2)), dv2 = ef_sub2(v2, ef_sub2(tv2, fl2));
                 const unsigned long long omdu2 = ef_sub2(one2, du2), omdv2 = ef_sub2(one2, dv2);
-                const unsigned short* __restrict__ qa = reinterpret_cast<const unsigned short*>(base + (via - oy) * EF_SIFT_WIN_PITCH) + (uia - ox);
-                const unsigned short* __restrict__ qb = reinterpret_cast<const unsigned short*>(base + (vib - oy) * EF_SIFT_WIN_PITCH) + (uib - ox);
+                float tua, tub, tva, tvb;
+                ef_unpack2(tu2, tua, tub); ef_unpack2(tv2, tva, tvb);
+                const unsigned short* __restrict__ qa = reinterpret_cast<const unsigned short*>(base + (__float_as_int(tva) - cv) * EF_SIFT_WIN_PITCH) + (__float_as_int(tua) - cu);
+                const unsigned short* __restrict__ qb = reinterpret_cast<const unsigned short*>(base + (__float_as_int(tvb) - cv) * EF_SIFT_WIN_PITCH) + (__float_as_int(tub) - cu);
                 const unsigned a0 = qa[0], a1 = qa[EF_SIFT_WIN_PITCH / 2], b0 = qb[0], b1 = qb[EF_SIFT_WIN_PITCH / 2];
-                const unsigned long long q00 = ef_pack2((float)(a0 & 0xffu), (float)(b0 & 0xffu)), q01 = ef_pack2((float)(a0 >> 8), (float)(b0 >> 8));
-                const unsigned long long q10 = ef_pack2((float)(a1 & 0xffu), (float)(b1 & 0xffu)), q11 = ef_pack2((float)(a1 >> 8), (float)(b1 >> 8));
+#define EF_B2F(w, sel) __uint_as_float(__byte_perm(w, 0x4B000000u, sel))
+                const unsigned long long q00 = ef_sub2(ef_pack2(EF_B2F(a0, 0x7440), EF_B2F(b0, 0x7440)), m23), q01 = ef_sub2(ef_pack2(EF_B2F(a0, 0x7441), EF_B2F(b0, 0x7441)), m23);
+                const unsigned long long q10 = ef_sub2(ef_pack2(EF_B2F(a1, 0x7440), EF_B2F(b1, 0x7440)), m23), q11 = ef_sub2(ef_pack2(EF_B2F(a1, 0x7441), EF_B2F(b1, 0x7441)), m23);
+#undef EF_B2F
                 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (seen in SASS); the reference rounds every
                 // product.  So each product is an FMA with a -0.0 addend that the compiler cannot see (x*y + -0.0 == round(x*y) bit for
                 // bit), and an FMA followed by an add is not fusable.
                 const unsigned long long tmp0 = ef_add2(ef_fma2(omdu2, q00, nz2), ef_fma2(du2, q01, nz2));
                 const unsigned long long tmp1 = ef_add2(ef_fma2(omdu2, q10, nz2), ef_fma2(du2, q11, nz2));
                 const unsigned long long tmp2 = ef_add2(ef_fma2(omdv2, tmp0, nz2), ef_fma2(dv2, tmp1, nz2));
+                // (uint8_t)min((int)(tmp2 + 0.5f), 255): tmp2 is a convex combination of bytes (<= 255 + rounding), so the truncation is the
+                // low byte of (tmp2 + 0.5f) + 2^23 rounded toward -infinity
                 float ra, rb;
-                ef_unpack2(ef_add2(tmp2, half2), ra, rb);
-                patch[y * 32 + hl] = (uint8_t)min(__float2int_rz(ra), 255);
-                patch[y * 32 + hl + 16] = (uint8_t)min(__float2int_rz(rb), 255);
+                ef_unpack2(ef_add2_rm(ef_add2(tmp2, half2), m23), ra, rb);
+                patch[y * 32 + hl] = (uint8_t)__float_as_uint(ra);
+                patch[y * 32 + hl + 16] = (uint8_t)__float_as_uint(rb);
             }
         }
         else if (inside) { EF_SIFT_SAMPLE_ROWS(false) } else { EF_SIFT_SAMPLE_ROWS(true) }
