@@ -37,13 +37,13 @@
 #define EF_SIFT_WIN_PITCH 136           // bytes per staged row: 64 pixels (48 + up to 15 alignment bytes), TWO bytes each -- entry x holds
                                         // (pixel x, pixel x+1), so a bilinear sample is two 16-bit loads; 34-word pitch spreads the banks
 #define EF_SIFT_PATCH_OFF 6464          // byte offset of the 32x32 u8 patch inside the keypoint block
-#define EF_SIFT_GB 8                    // gradient pixels per lane and step (gathers in flight; 16: +0.3 %, measured)
+#define EF_SIFT_GROWS 5                 // gradient rows per lane and step (10 table gathers in flight)
 
 // Shared memory of one warp = 2 keypoints: 16 128 bytes, so that SEVEN 2-warp CTAs fit one SM (2 x 16128 + 1024 reserved = 33280 = 130 x 256-byte allocation units, 7 x 33280 <= 233472;
 // 18.9 KB per warp gave six).  One block per keypoint is used three times over:
 //   staging   bytes [0, 46 x 136) the 46 x 64 window, while the sampler writes the patch at [PATCH_OFF, PATCH_OFF + 1024)
 //   gradients magnitude[i] at float k + i (sign bit = bin bit 2), fraction[i] at float REC + k + i (bits 31:30 = bin bits 1:0), written
-//             in steps of 128 pixels while the patch is still being read: the fraction records of pixel i >= 704 land ON the patch, at
+//             in steps of EF_SIFT_GROWS pixel rows while the patch is still being read: the fraction records of rows >= 23 land ON the patch, at
 //             patch byte 4 (i + k + 916) - PATCH_OFF, always in rows that no later step reads (tests/test_layout_hashsift.py replays the
 //             schedule); inside a step every lane reads before any lane writes (__syncwarp)
 //   histogram records read only; afterwards the first 128 floats hold the descriptor being normalised
@@ -56,6 +56,14 @@ static_assert(sizeof(EfSiftWarpSmem) == 16128 && 7 * (EF_SIFT_WARPS * sizeof(EfS
 static_assert(EF_SIFT_WIN_ROWS * EF_SIFT_WIN_PITCH <= EF_SIFT_PATCH_OFF, "the staged window must end below the patch");
 static_assert(EF_SIFT_PATCH_OFF % 16 == 0 && EF_SIFT_PATCH_OFF + 1024 <= EF_SIFT_BLK * 4, "patch inside the block");
 static_assert(4 * (2 * EF_SIFT_REC + 1) <= EF_SIFT_BLK * 4 && EF_SIFT_BLK % 4 == 0, "both record arrays inside the block");
+
+// sum of the four unsigned bytes of a times the four signed bytes of coeff
+__device__ __forceinline__ int ef_dot4_u8s8(unsigned a, unsigned coeff)
+{
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(coeff), "r"(0));
+    return r;
+}
 
 // normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
 __device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
@@ -209,34 +217,50 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
     }
     __syncwarp();
     // ---- per-pixel magnitude / orientation (hash_sift.cpp:247-260) through the finite-domain tables (ef_api.cu).
-    //      Eight pixels per lane and step, in three explicit stages (patch reads, table gathers, record writes) so that the
-    //      eight gathers are in flight together instead of one global round trip per pixel.
+    //      Lane hl < 15 owns the gradient columns 2 hl and 2 hl + 1 and walks the 30 rows; the four patch bytes [2 hl, 2 hl + 3] of a row serve
+    //      the row above (as "below"), its own row's left/right neighbours and the row below (as "above"), so every patch row is loaded once
+    //      and kept in a rolling register window; the four differences are byte dot products (IDP.4A), every index is a compile-time
+    //      offset from a per-lane base.  EF_SIFT_GROWS rows per step: patch loads, then 2 x GROWS table gathers in flight, then the records.
     {
         float* __restrict__ magp = blk + k;
         float* __restrict__ ofp = blk + EF_SIFT_REC + k;
-        constexpr int GB = EF_SIFT_GB;
-        for (int s0 = 0; s0 < 900; s0 += 16 * GB) {         // warp-uniform trip count: the __syncwarp below is reached by all lanes
-            const int i0 = s0 + hl;
-            int tix[GB], rix[GB], pix[GB];
+        constexpr int R = EF_SIFT_GROWS;
+        static_assert(30 % R == 0, "whole steps");
+        const int xl = min(2 * hl, 28);                         // lane 15 shadows lane 14 (its stores are skipped)
+        const bool act = hl < 15;
+        const uint8_t* __restrict__ prow = patch + xl;
+        const float2* __restrict__ gt = t.grad_table + (255 * 511 + 255);
+        const float2* __restrict__ et = reinterpret_cast<const float2*>(t.exp_table + xl);
+        auto row4 = [&](int r) {
+            const unsigned lo = *reinterpret_cast<const unsigned short*>(prow + 32 * r), hi = *reinterpret_cast<const unsigned short*>(prow + 32 * r + 2);
+            return __byte_perm(lo, hi, 0x5410);
+        };
+        unsigned rw[R + 2];
+        rw[0] = row4(0); rw[1] = row4(1);
 #pragma unroll
-            for (int u = 0; u < GB; u++) {
-                const int i = min(i0 + 16 * u, 899);          // lanes past the end repeat pixel 899 (their writes are skipped)
-                const int y = (i * 1093) >> 15, x = i - 30 * y; // i / 30 for i < 1024
-                const uint8_t* c = patch + (y + 1) * 32 + x + 1;
-                const int dxi = (int)c[1] - (int)c[-1];
-                const int dyi = (int)c[-32] - (int)c[32];
-                tix[u] = (dyi + 255) * 511 + (dxi + 255);
-                rix[u] = i + 2 * (y >> 3);
-                pix[u] = i;
+        for (int y0 = 0; y0 < 30; y0 += R) {
+#pragma unroll
+            for (int j = 0; j < R; j++) rw[j + 2] = row4(y0 + j + 2);
+            float2 e[2 * R], ew[R];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const unsigned above = rw[j], centre = rw[j + 1], below = rw[j + 2];
+                const int dxa = ef_dot4_u8s8(centre, 0x000100FFu), dxb = ef_dot4_u8s8(centre, 0x0100FF00u);           // c[1] - c[-1]
+                const unsigned ab = __byte_perm(above, below, 0x6521);                                         // (above[1], above[2], below[1], below[2])
+                const int dya = ef_dot4_u8s8(ab, 0x00FF0001u), dyb = ef_dot4_u8s8(ab, 0xFF000100u);               // c[-32] - c[32]
+                e[2 * j] = __ldg(gt + (dya * 511 + dxa));
+                e[2 * j + 1] = __ldg(gt + (dyb * 511 + dxb));
+                ew[j] = __ldg(et + 15 * (y0 + j));
             }
-            float2 e[GB];
-            float ew[GB];
+            rw[0] = rw[R]; rw[1] = rw[R + 1];
+            __syncwarp();                                       // late fraction records overwrite patch rows (read long before: see the test)
+            if (act) {
 #pragma unroll
-            for (int u = 0; u < GB; u++) { e[u] = __ldg(t.grad_table + tix[u]); ew[u] = __ldg(t.exp_table + pix[u]); }
-            __syncwarp();                                       // late fraction records overwrite patch rows this step has just read
-#pragma unroll
-            for (int u = 0; u < GB; u++) {
-                if (i0 + 16 * u < 900) { magp[rix[u]] = ew[u] * e[u].x; ofp[rix[u]] = e[u].y; }
+                for (int j = 0; j < R; j++) {
+                    const int y = y0 + j, rix = y * 30 + 2 * (y >> 3) + xl;
+                    magp[rix] = ew[j].x * e[2 * j].x; ofp[rix] = e[2 * j].y;
+                    magp[rix + 1] = ew[j].y * e[2 * j + 1].x; ofp[rix + 1] = e[2 * j + 1].y;
+                }
             }
         }
     }
