@@ -37,7 +37,7 @@
 #define EF_SIFT_WIN_PITCH 136           // bytes per staged row: 64 pixels (48 + up to 15 alignment bytes), TWO bytes each -- entry x holds
                                         // (pixel x, pixel x+1), so a bilinear sample is two 16-bit loads; 34-word pitch spreads the banks
 #define EF_SIFT_PATCH_OFF 6464          // byte offset of the 32x32 u8 patch inside the keypoint block
-#define EF_SIFT_GROWS 5                 // gradient rows per lane and step (10 table gathers in flight)
+#define EF_SIFT_GROWS 5                 // gradient rows per lane and step (10 table gathers in flight; 10 rows: the same time, measured)
 
 // Shared memory of one warp = 2 keypoints: 16 128 bytes, so that SEVEN 2-warp CTAs fit one SM (2 x 16128 + 1024 reserved = 33280 = 130 x 256-byte allocation units, 7 x 33280 <= 233472;
 // 18.9 KB per warp gave six).  One block per keypoint is used three times over:
@@ -65,21 +65,26 @@ __device__ __forceinline__ int ef_dot4_u8s8(unsigned a, unsigned coeff)
     return r;
 }
 
-// normalize(), hash_sift.cpp:150-160: sequential sum, every lane of the half-warp computes it redundantly
-__device__ __forceinline__ void ef_sift_normalize(float* d, int hl)
+// normalize(), hash_sift.cpp:150-160.  Lane hl keeps the eight bins of its cell (descriptor elements 8 hl .. 8 hl + 7) in registers; the sum of
+// squares is sequential (one chain of 128 additions, computed redundantly by every lane of the half-warp) over the squares, which are
+// formed once, eight per lane, into the scratch sq[128].
+__device__ __forceinline__ void ef_sift_normalize(float (&v)[8], float* sq, int hl)
 {
+    float4* sq4 = reinterpret_cast<float4*>(sq);
+    sq4[2 * hl] = make_float4(v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]);
+    sq4[2 * hl + 1] = make_float4(v[4] * v[4], v[5] * v[5], v[6] * v[6], v[7] * v[7]);
+    __syncwarp();
     float sum = 0.f;
-    const float4* d4 = reinterpret_cast<const float4*>(d);
 #pragma unroll 8
     for (int i = 0; i < 32; i++) {
-        const float4 v = d4[i];
-        sum += v.x * v.x; sum += v.y * v.y; sum += v.z * v.z; sum += v.w * v.w;
+        const float4 q = sq4[i];
+        sum += q.x; sum += q.y; sum += q.z; sum += q.w;
     }
+    __syncwarp();                       // every lane has read the squares before the next call overwrites them
     const float nrm = fmaxf(sqrtf(sum), FLT_EPSILON);
     const float scale = 1.f / nrm;
-    __syncwarp();
-    for (int i = hl; i < 128; i += 16) d[i] *= scale;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] *= scale;
 }
 
 // All 32 lanes call this; lanes 0-15 work on keypoint slot 0 of the warp, lanes 16-31 on slot 1.
@@ -301,10 +306,12 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                     unsigned ofv[16];
 #pragma unroll
                     for (int xo = 1; xo < 16; xo++) {
+                        // out-of-patch visit: an all-zero record without touching memory (predicated loads at a fixed offset from the row base)
                         const bool ok = rowok && (unsigned)(xb + xo) < 30u;
-                        const int idx = ok ? rowidx + xo : EF_SIFT_ZERO;
-                        mgv[xo] = mp[idx];
-                        const unsigned ob = op[idx];
+                        float mg0 = 0.f;
+                        unsigned ob = 0u;
+                        if (ok) { mg0 = mp[rowidx + xo]; ob = op[rowidx + xo]; }
+                        mgv[xo] = mg0;
                         hoff[xo] = ((ob >> 30) | ((__float_as_uint(mgv[xo]) >> 31) << 2)) * 32u;
                         ofv[xo] = ob & 0x3fffffffu;
                     }
@@ -366,26 +373,21 @@ __device__ __forceinline__ void ef_hashsift_one(const uint8_t* __restrict__ img,
                 }
             }
         }
-        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: the bin number is <= 7); the descriptor takes
-        // the place of the first records once every lane is done with them
-        __syncwarp();
-        float* d = blk + hl * 8;
-        d[0] = hc[0] + hc[8 * 32];
+        // circular fold (hash_sift.cpp:299-302): bin0 += bin8 (bin 9 is never written: the bin number is <= 7)
+        float v[8];
+        v[0] = hc[0] + hc[8 * 32];
 #pragma unroll
-        for (int b = 1; b < 8; b++) d[b] = hc[b * 32];
-    }
-    __syncwarp();
-    // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
-    float* desc = blk;
-    ef_sift_normalize(desc, hl);
-    for (int i = hl; i < 128; i += 16) desc[i] = fminf(desc[i], 0.2f);
-    __syncwarp();
-    ef_sift_normalize(desc, hl);
-    {
+        for (int b = 1; b < 8; b++) v[b] = hc[b * 32];
+        __syncwarp();                   // every lane is done with the records: their first 128 floats become the squares scratch
+        // ---- L2 normalise, clip 0.2, renormalise, x512 -> uchar (hash_sift.cpp:311-330)
+        ef_sift_normalize(v, blk, hl);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = fminf(v[j], 0.2f);
+        ef_sift_normalize(v, blk, hl);
         unsigned packed[2] = { 0, 0 };
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int q = __float2int_rn(512.f * desc[hl * 8 + j]);
+            const int q = __float2int_rn(512.f * v[j]);
             packed[j >> 2] |= (unsigned)min(max(q, 0), 255) << (8 * (j & 3));
         }
         if (store) reinterpret_cast<uint2*>(out128)[hl] = make_uint2(packed[0], packed[1]);
