@@ -115,3 +115,42 @@ def test_random_compute_only_matches_oracle(torch_cuda, oracle, case):
         o = oracle.hashsift(img, k, scale, nbits)
     bad = (g != o).any(axis=1)
     assert not bad.any(), f"case {case}: {bad.sum()} of {n} descriptors differ ({w}x{h}, scale {scale}, {nbits} bits), first keypoint {k[np.nonzero(bad)[0][0]]}"
+
+
+N_MATCH = int(os.environ.get("EF_FUZZ_MATCH_CASES", "16"))
+
+
+@pytest.mark.parametrize("case", range(N_MATCH))
+def test_random_matcher_and_ingest_match_oracle(torch_cuda, case):
+    """Hamming matcher (knn k = 2, best match, cross-check, ratio + cross-check filter) and BGR(A) -> gray on random shapes: query / train
+    counts from 1 to a few thousand (tile remainders of the tcgen05 kernel, fewer train rows than k), 256- and 512-bit rows, a small byte
+    alphabet for masses of ties, duplicated rows."""
+    import efb200
+    import match_oracle as mo
+    torch = torch_cuda
+    rng = np.random.default_rng(0xEFB2A000 + case)
+    nq, nt = int(rng.choice([1, 2, 31, 129, 500, 1025, 3000])), int(rng.choice([1, 2, 33, 127, 128, 777, 2049, 4000]))
+    nbytes, lo = int(rng.choice([32, 64])), int(rng.choice([2, 4, 256]))
+    q = rng.integers(0, lo, (nq, nbytes), dtype=np.uint8)
+    t = rng.integers(0, lo, (nt, nbytes), dtype=np.uint8)
+    if nt > 4 and case % 3 == 0:
+        t[rng.integers(0, nt, nt // 4)] = t[rng.integers(0, nt, nt // 4)]          # duplicated train rows: equal distances, lowest index wins
+    if nq > 4 and nt > 4 and case % 4 == 1:
+        q[: min(nq, nt) // 2] = t[: min(nq, nt) // 2]                               # exact matches (distance 0)
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    bf = efb200.BFMatcher.create()
+    i12, d12 = bf.knnMatchAsync(dq, dt, 2); i21, d21 = bf.knnMatchAsync(dt, dq, 2)
+    oi12, od12 = mo.knn_match(q, t, 2); oi21, od21 = mo.knn_match(t, q, 2)
+    assert np.array_equal(i12.cpu().numpy(), oi12), f"case {case}: knn indices differ ({nq} x {nt} x {nbytes})"
+    v12, v21 = oi12 >= 0, oi21 >= 0
+    assert np.array_equal(d12.cpu().numpy()[v12], od12[v12])
+    assert np.array_equal(i21.cpu().numpy(), oi21) and np.array_equal(d21.cpu().numpy()[v21], od21[v21])
+    ci, cd = efb200.BFMatcher.create(efb200.NORM_HAMMING, True).matchAsync(dq, dt)
+    oci, ocd = mo.cross_check_match(q, t)
+    assert np.array_equal(ci.cpu().numpy(), oci) and np.array_equal(cd.cpu().numpy()[oci >= 0], ocd[oci >= 0])
+    if nq >= 2 and nt >= 2:
+        f = efb200.ratio_cross_filter(i12, d12, i21, d21, 0.9)
+        assert np.array_equal(f.cpu().numpy(), mo.ratio_cross_filter(oi12, od12, oi21, od21, 0.9))
+    h, w, cn = int(rng.integers(1, 300)), int(rng.integers(1, 500)), int(rng.choice([3, 4]))
+    img = rng.integers(0, 256, (h, w, cn), dtype=np.uint8)
+    assert np.array_equal(efb200.cvtColorToGray(torch.from_numpy(img).cuda()).cpu().numpy(), mo.bgr_to_gray(img))
