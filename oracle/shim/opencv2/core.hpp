@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <chrono>
+#include <type_traits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -82,8 +83,12 @@ template <typename T, typename... A> Ptr<T> makePtr(A&&... a) { return std::make
 template <typename T> struct Point_
 {
     T x, y; Point_() : x(0), y(0) {} Point_(T a, T b) : x(a), y(b) {}
+    template <typename U> Point_(const Point_<U>& o) : x(saturate_point<T>(o.x)), y(saturate_point<T>(o.y)) {}   // Point2f -> Point rounds, like OpenCV
     Point_& operator*=(T s) { x *= s; y *= s; return *this; }
+private:
+    template <typename V, typename U> static V saturate_point(U v) { return std::is_integral<V>::value && !std::is_integral<U>::value ? (V)lrint((double)v) : (V)v; }
 };
+typedef Point_<int> Point;
 template <typename T, int N> struct Vec
 {
     T val[N];
@@ -95,7 +100,13 @@ template <typename T, int N> struct Vec
 };
 typedef Vec<short, 2> Vec2s;
 typedef Vec<float, 4> Vec4f;
-struct Scalar { double val[4]; static Scalar all(double v) { Scalar s; for (double& x : s.val) x = v; return s; } };
+struct Scalar
+{
+    double val[4];
+    Scalar() : val{ 0, 0, 0, 0 } {}
+    Scalar(double a, double b = 0, double c = 0, double d = 0) : val{ a, b, c, d } {}
+    static Scalar all(double v) { return Scalar(v, v, v, v); }
+};
 struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = FLT_MAX; };
 struct Range { int start, end; Range(int s, int e) : start(s), end(e) {} };
 typedef Point_<float> Point2f;
@@ -325,6 +336,20 @@ static inline String format(const char* fmt, ...)
     va_list ap; va_start(ap, fmt); std::vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
     return String(buf);
 }
+
+// cv::TickMeter (samples/sample_image_sequence.cpp:96-103)
+class TickMeter
+{
+public:
+    void start() { t0_ = std::chrono::steady_clock::now(); }
+    void stop() { total_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0_).count(); n_++; }
+    void reset() { total_ = 0; n_ = 0; }
+    double getTimeSec() const { return total_; }
+    double getTimeMilli() const { return total_ * 1e3; }
+    long getCounter() const { return n_; }
+private:
+    std::chrono::steady_clock::time_point t0_; double total_ = 0; long n_ = 0;
+};
 
 // cv::CommandLineParser for key strings of the form "{ name alias | default | help }" (samples/sample_benchmark.cpp:27-37)
 class CommandLineParser

@@ -25,4 +25,7 @@ static inline Mat imread(const String& filename, int = IMREAD_COLOR)
     if (try_pgm(filename, img) || try_pgm(filename + ".pgm", img)) return img;
     return Mat();
 }
+// no display: imshow reports what it was given, waitKey returns "no key"
+static inline void imshow(const String& name, const Mat& img) { std::cout << "[imshow] " << name << " " << img.cols << "x" << img.rows << "x" << img.channels() << std::endl; }
+static inline int waitKey(int = 0) { return -1; }
 } // namespace cv
