@@ -12,6 +12,7 @@
 // absdiff / countNonZero, format, CommandLineParser; cv::cuda::GpuMat / Stream live in core/cuda.hpp (pulled in only when
 // the CUDA runtime headers are on the include path).  None of this is product code.
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -68,6 +69,8 @@ static inline int cvRound(float v) { return (int)lrintf(v); }
 static inline int cvRound(double v) { return (int)lrint(v); }
 static inline int cvFloor(float v) { int i = (int)v; return i - (i > v); }
 static inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
+static inline int cvCeil(float v) { int i = (int)v; return i + (i < v); }
+static inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
 
 namespace cv
 {
@@ -199,8 +202,10 @@ public:
     template <typename T> T& at(int i) { return *(T*)(data + (size_t)i * step.p[0]); }
     template <typename T> const T& at(int i) const { return *(const T*)(data + (size_t)i * step.p[0]); }
     bool isContinuous() const { return dims != 2 || step.p[0] == (size_t)cols * elemSize(); }
+    size_t step1(int i = 0) const { static const int d[8] = { 1, 1, 2, 2, 4, 4, 8, 2 }; return step.p[i] / (size_t)d[type_ & 7]; }
     Mat colRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * elemSize(); m.cols = b - a; m.size_[1] = b - a; return m; }
     Mat rowRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * step.p[0]; m.rows = b - a; m.size_[0] = b - a; return m; }
+    Mat rowRange(const Range& r) const { return rowRange(r.start, r.end); }
     void copyTo(Mat& dst) const
     {
         CV_Assert(dims == 2);
@@ -329,6 +334,34 @@ static inline int countNonZero(const Mat& a)
     int n = 0;
     for (int i = 0; i < a.rows; i++) { const uchar* p = a.ptr<uchar>(i); for (int j = 0; j < a.cols; j++) n += p[j] != 0; }
     return n;
+}
+// cv::hconcat of equally tall 2-D matrices of one type (samples/hpatches_description.cpp:222-223)
+static inline void hconcat(const std::vector<Mat>& src, Mat& dst)
+{
+    CV_Assert(!src.empty());
+    int cols = 0;
+    for (const Mat& m : src) { CV_Assert(m.dims == 2 && m.rows == src[0].rows && m.type() == src[0].type()); cols += m.cols; }
+    Mat out(src[0].rows, cols, src[0].type());
+    const size_t es = out.elemSize();
+    for (int y = 0; y < out.rows; y++) {
+        uchar* d = out.ptr<uchar>(y);
+        for (const Mat& m : src) { std::memcpy(d, m.ptr<uchar>(y), (size_t)m.cols * es); d += (size_t)m.cols * es; }
+    }
+    dst = out;
+}
+// cv::fastAtan2, scalar form: the 7th-order odd polynomial of OpenCV's mathfuncs_core (degrees, [0, 360)); restated from the published
+// algorithm and pinned against cv2.fastAtan2 by tests/test_hpatches_tool.py (through oracle/_ref/fastatan2_check)
+static inline float fastAtan2(float y, float x)
+{
+    const float scale = (float)(180 / CV_PI);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float ax = std::abs(x), ay = std::abs(y);
+    float a, c, c2;
+    if (ax >= ay) { c = ay / (ax + (float)DBL_EPSILON); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    else { c = ax / (ay + (float)DBL_EPSILON); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
 }
 static inline String format(const char* fmt, ...)
 {

@@ -80,3 +80,53 @@ def test_descriptors_equal_oracle(tmp_path, oracle, desc_type, bits, angle):
             rows = (res / f"{hp.DESC_STR[desc_type]}_{bits}" / seq.name / (f.stem + ".csv")).read_text().strip().split("\n")
             got = np.packbits(np.array([[int(b) for b in r.split(",")] for r in rows], np.uint8), axis=1)
             assert np.array_equal(got, want[x * npatches:(x + 1) * npatches]), f"{seq.name}/{f.name}"
+
+
+# ---- the reference's own UNMODIFIED samples/hpatches_description.cpp over the adapter (oracle/_ref/ref_hpatches_description)
+REFBIN = ROOT / "oracle" / "_ref"
+
+
+def test_standin_fastatan2_equals_cv2():
+    """cv::fastAtan2 of the OpenCV stand-in (used by the reference sample's ICAngles) == cv2.fastAtan2, bit for bit"""
+    cv2 = pytest.importorskip("cv2")
+    import subprocess
+    exe = REFBIN / "fastatan2_check"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/fastatan2_check not built (make -C oracle adapter)")
+    rng = np.random.default_rng(5)
+    y = np.concatenate([rng.integers(-70000, 70000, 4000).astype(np.float32), np.array([0, 0, 1, -1, 5, -5, 0, 3e-9, 1e9], np.float32)])
+    x = np.concatenate([rng.integers(-70000, 70000, 4000).astype(np.float32), np.array([0, 1, 0, 0, 5, 5, -2, 1e-9, -1e9], np.float32)])
+    out = subprocess.run([str(exe)], input="".join(f"{float(a)!r} {float(b)!r}\n" for a, b in zip(y, x)), capture_output=True, text=True, timeout=60)
+    got = np.array([int(l) for l in out.stdout.split()], np.uint32).view(np.float32)
+    want = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.nonzero(got != want)[0][:5]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("desc_type,bits,angle", [(0, 256, True), (1, 512, False), (1, 256, True)])
+def test_reference_hpatches_sample_equals_the_tool(tmp_path, desc_type, bits, angle):
+    """the reference's sample (cv::imread stand-in reads "<strip>.png.pgm") and tools/hpatches_description.py --directory-order write the
+    same CSV files"""
+    cv2 = pytest.importorskip("cv2")
+    import subprocess
+    exe = REFBIN / "ref_hpatches_description"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_hpatches_description not built (needs /root/reference at build time)")
+    hp = _tool()
+    data, res_tool, res_ref = tmp_path / "hpatches", tmp_path / "result_tool", tmp_path / "result_ref"
+    flags = ["--descriptor-type", str(desc_type), "--descriptor-bits", str(bits)] + (["--compute-angle"] if angle else [])
+    hp.write_synthetic(data, 2)
+    for png in list(data.rglob("*.png")):
+        img = cv2.imread(str(png), cv2.IMREAD_GRAYSCALE)
+        with open(str(png) + ".pgm", "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0])); f.write(img.tobytes())
+    out = subprocess.run([str(exe), str(data), f"--result-dir={res_ref}", f"--descriptor-type={desc_type}", f"--descriptor-bits={bits}"] +
+                         (["--compute-angle"] if angle else []), capture_output=True, text=True, cwd=ROOT, timeout=600)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    # the reference concatenates the strips in readdir order, and a rotated 64-pixel patch reaches into the neighbouring strips
+    assert hp.main([str(data), "--result-dir", str(res_tool), "--directory-order"] + flags) == 0
+    csvs = sorted(p.relative_to(res_tool) for p in res_tool.rglob("*.csv"))
+    assert len(csvs) == 8 and csvs == sorted(p.relative_to(res_ref) for p in res_ref.rglob("*.csv"))
+    for c in csvs:
+        assert (res_tool / c).read_text() == (res_ref / c).read_text(), str(c)

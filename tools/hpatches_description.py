@@ -12,9 +12,11 @@ descriptors come from EfficientFeatures::compute with the vector<KeyPoint> argum
 ef_compute_async behind efb200.EfficientFeatures.compute) and are written as one CSV of 0/1 per strip, most
 significant bit first (:76-105), under <result-dir>/<BAD|HashSIFT>_<bits>/<sequence>/<strip>.csv.
 
-Differences from the reference, on purpose: strips are taken in sorted order (std::filesystem::directory_iterator
-has none); `--synthetic S` writes S small synthetic sequences into <hpatches-release> first (the dataset is not
-redistributable and absent here; tests/test_hpatches_tool.py uses it).
+Differences from the reference, on purpose: strips are taken in sorted order -- the reference concatenates them in the order
+std::filesystem::directory_iterator yields (:55-63, unsorted), and with --compute-angle a rotated 64-pixel patch reaches into the
+neighbouring strips, so its output depends on that file-system order; `--directory-order` reproduces it (os.listdir walks the same
+readdir sequence; tests/test_hpatches_tool.py compares this tool with the reference's own unmodified sample that way).  `--synthetic S`
+writes S small synthetic sequences into <hpatches-release> first (the dataset is not redistributable and absent here).
 
 Image files are decoded with cv2 (the reference uses cv::imread); everything numeric on the descriptor side runs
 in libef_b200.so on the GPU -- there is no CPU fallback."""
@@ -102,9 +104,12 @@ def descriptor_csv(desc: np.ndarray) -> str:
     return "".join(",".join(map(str, row)) + "\n" for row in bits.tolist())
 
 
-def load_sequence(seq_dir: Path):
+def load_sequence(seq_dir: Path, directory_order: bool = False):
     import cv2
-    files = sorted(p for p in seq_dir.iterdir() if p.suffix == ".png")
+    if directory_order:
+        files = [seq_dir / n for n in os.listdir(seq_dir) if n.endswith(".png")]
+    else:
+        files = sorted(p for p in seq_dir.iterdir() if p.suffix == ".png")
     images = [cv2.imread(str(p), cv2.IMREAD_GRAYSCALE) for p in files]
     if any(i is None for i in images):
         raise RuntimeError(f"could not read every strip of {seq_dir}")
@@ -148,6 +153,7 @@ def main(argv=None) -> int:
     ap.add_argument("--descriptor-type", type=int, default=0, help="descriptor type(0:BAD 1:HashSIFT).")
     ap.add_argument("--descriptor-bits", type=int, default=256, help="descriptor bits(256 or 512).")
     ap.add_argument("--compute-angle", action="store_true", help="compute angles of keypoints.")
+    ap.add_argument("--directory-order", action="store_true", help="concatenate the strips in directory (readdir) order like the reference instead of sorted")
     ap.add_argument("--synthetic", type=int, default=0, metavar="S", help="first write S synthetic sequences into hpatches_dir")
     a = ap.parse_args(argv)
 
@@ -168,7 +174,7 @@ def main(argv=None) -> int:
     desc_dir = Path(a.result_dir) / f"{DESC_STR[a.descriptor_type]}_{a.descriptor_bits}"
     for count, seq in enumerate(seqs, 1):
         print(f"sequence: {count:3d}/{len(seqs):3d} [{seq.name}]")
-        files, images = load_sequence(seq)
+        files, images = load_sequence(seq, a.directory_order)
         _, kpts, desc = describe_sequence(images, a.descriptor_type, a.descriptor_bits, a.compute_angle)
         npatches = len(kpts) // len(images)
         print(f"patch num: [{npatches} x {len(images)}]\n")
