@@ -918,16 +918,19 @@ __global__ void __launch_bounds__(256, 8) ef_nms_kernel(const __grid_constant__ 
             bool kill = false;
             if (cand) {
                 int wy = part / wside, wx = part - wy * wside;
-                for (int n = part; n < nnb; n += 4) {
-                    if (n != (nnb >> 1)) {                                    // the centre of the window is the block itself
-                        const EfBlockMax e = s_blk[nbase + wy * side_x + wx];
-                        if (e.val >= r) {
-                            const int ex = (int)(e.pos & 0xffff) - cx, ey = (int)((e.pos >> 16) & 0x7fff) - cy;
-                            if (ex * ex + ey * ey < r2) kill = true;
-                        }
-                    }
+                // branch-free body (on noise about half of the neighbouring maxima are >= r: a branch diverges anyway); with the block
+                // reach known at compile time the walk is unrolled
+                constexpr int NNB = TB ? (2 * TK + 1) * (2 * TK + 1) : 0;
+#pragma unroll
+                for (int j = 0; j < (TB ? (NNB + 3) / 4 : 0x7fffffff); j++) {
+                    const int n = part + 4 * j;
+                    if (n >= nnb) break;
+                    const EfBlockMax e = s_blk[nbase + wy * side_x + wx];
+                    const int ex = (int)(e.pos & 0xffff) - cx, ey = (int)((e.pos >> 16) & 0x7fff) - cy;
+                    kill |= (n != (nnb >> 1)) & (e.val >= r) & (ex * ex + ey * ey < r2);   // the centre of the window is the block itself
                     wx += 4;
-                    while (wx >= wside) { wx -= wside; wy++; }
+                    if (wx >= wside) { wx -= wside; wy++; }          // wside >= 5 (K >= 2): one wrap at most; wside == 3: possibly two
+                    if (wside < 5 && wx >= wside) { wx -= wside; wy++; }
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, kill);
@@ -950,7 +953,8 @@ __global__ void __launch_bounds__(256, 8) ef_nms_kernel(const __grid_constant__ 
                         }
                     }
                     wx += 4;
-                    while (wx >= wside) { wx -= wside; wy++; }
+                    if (wx >= wside) { wx -= wside; wy++; }          // wside >= 5 (K >= 2): one wrap at most; wside == 3: possibly two
+                    if (wside < 5 && wx >= wside) { wx -= wside; wy++; }
                 }
             }
             __syncthreads();
