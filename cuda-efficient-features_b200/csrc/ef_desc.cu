@@ -148,8 +148,11 @@ __device__ __forceinline__ EfBadAffine ef_bad_affine(float kx, float ky, float s
 
 // integral accessors.  box(y0, x0, y1, x1) = sum of the pixels in rows [y0, y1) x columns [x0, x1)
 struct EfGlobalIntegral { // (h+1) x (w+1) uint32 integral image of the whole frame (wrapping arithmetic, exact differences)
-    const unsigned* I; int iw;
-    __device__ __forceinline__ unsigned at(int y, int x) const { return __ldg(I + (size_t)y * iw + x); }
+    const unsigned* I; int iw, ih;
+    // A keypoint closer to the image edge than its largest box, yet not "in the border" by bad.cpp:92-102 (the test scales with the
+    // keypoint size: size 2 on the last row passes it), makes the reference read past its integral image -- undefined there.  Here,
+    // and in the oracle, such reads are clamped to the last row / column of the integral image: defined, and never out of the buffer.
+    __device__ __forceinline__ unsigned at(int y, int x) const { return __ldg(I + (size_t)min(max(y, 0), ih - 1) * iw + min(max(x, 0), iw - 1)); }
     __device__ __forceinline__ unsigned box(int y0, int x0, int y1, int x1) const { return at(y0, x0) + at(y1, x1) - at(y0, x1) - at(y1, x0); }
 };
 // 16-bit modular integral of the 48-row window around a keypoint (ef_bad_pipe_kernel): P[r][a] (halfword r*PITCH + a) =
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(EF_DESC_WARPS * 32) ef_bad_flat_kernel(const E
     if (i >= job.n) return;
     const float4 k = job.kpts[i];
     const EfBadAffine a = ef_bad_affine(k.x, k.y, k.z, k.w, job.scale, job.w, job.h);
-    EfGlobalIntegral I; I.I = integral; I.iw = job.w + 1;
+    EfGlobalIntegral I; I.I = integral; I.iw = job.w + 1; I.ih = job.h + 1;
     ef_bad_describe(I, a, t, job.nbits, job.w, job.h, job.desc + (size_t)i * job.desc_pitch, lane);
 }
 

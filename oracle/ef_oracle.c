@@ -448,9 +448,13 @@ void efo_bad_compute(const uint8_t* img, int w, int h, size_t pitch, const efo_k
                 const int x1a = o.x1 - o.r, y1a = o.y1 - o.r, x1b = o.x1 + o.r + 1, y1b = o.y1 + o.r + 1;
                 const int x2a = o.x2 - o.r, y2a = o.y2 - o.r, x2b = o.x2 + o.r + 1, y2b = o.y2 + o.r + 1;
                 const int side = 1 + (o.r << 1);
-                const uint32_t acc = I[(size_t)y1a * iw + x1a] + I[(size_t)y1b * iw + x1b] - I[(size_t)y1a * iw + x1b] -
-                                     I[(size_t)y1b * iw + x1a] - I[(size_t)y2a * iw + x2a] - I[(size_t)y2b * iw + x2b] +
-                                     I[(size_t)y2a * iw + x2b] + I[(size_t)y2b * iw + x2a];
+                /* A keypoint closer to the edge than its largest box that still passes the (size-scaled) border test makes the reference
+                 * read past its integral image: undefined there.  DEFINED here (and in the CUDA path): indices clamp to the last row /
+                 * column of the integral image. */
+#define EFO_I(y_, x_) I[(size_t)((y_) < 0 ? 0 : (y_) > h ? h : (y_)) * iw + ((x_) < 0 ? 0 : (x_) > w ? w : (x_))]
+                const uint32_t acc = EFO_I(y1a, x1a) + EFO_I(y1b, x1b) - EFO_I(y1a, x1b) - EFO_I(y1b, x1a)
+                                   - EFO_I(y2a, x2a) - EFO_I(y2b, x2b) + EFO_I(y2a, x2b) + EFO_I(y2b, x2a);
+#undef EFO_I
                 bit = (float)(int32_t)acc <= (thr * (float)(side * side));
             }
             byte |= (uint8_t)(bit << bit_idx);

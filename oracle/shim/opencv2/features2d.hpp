@@ -31,6 +31,9 @@ static inline void drawMatches(InputArray img1, const std::vector<KeyPoint>&, In
 // cv::BFMatcher(NORM_HAMMING) as the reference's samples use it (sample_feature_matching.cpp:99-101: create(NORM_HAMMING, true)->match;
 // sample_image_sequence.cpp:81,115-116: create(defaultNorm())->knnMatch k = 2), routed to the library's matcher through the C ABI
 // (ef_match_cross_check_async / ef_match_knn_async): the substitution INTEGRATION.md proposes for the step after the path.
+// Compiled only into the adapter binaries (-DEF_SHIM_WITH_MATCHER, oracle/Makefile): the CPU-only builds of the reference's descriptor sources
+// include this header too and have neither the CUDA runtime nor include/ on their path.
+#ifdef EF_SHIM_WITH_MATCHER
 #include <cuda_runtime.h>
 #include "ef_b200.h"
 namespace cv
@@ -85,3 +88,4 @@ private:
     bool cross_;
 };
 } // namespace cv
+#endif // EF_SHIM_WITH_MATCHER
