@@ -871,13 +871,14 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
             plan.emplace_back(f, c); f += c;
         }
     } else if (h->host_chunk <= 0) {
-        // geometric plan (EF_B200_HOST_CHUNK=0): 1, 2, 4, 8, 16, 16, ... frames -- the kernels start after ONE frame is up, every later chunk is
-        // uploaded while the previous (half as large) one computes, launches per frame fall -- and a one-frame tail, so that only
-        // 2.5 MB of results are still to be downloaded when the last kernel ends
+        // growing plan (EF_B200_HOST_CHUNK=0): 1, 3, 6, 12, 12, ... frames -- the kernels start after ONE frame is up, every later chunk is
+        // uploaded while the previous (smaller) one computes, launches per frame fall -- and a one-frame tail, so that only 2.5 MB of
+        // results are still to be downloaded when the last kernel ends.  Measured at 32 frames (tools/gpu_e2e_plan.sh, ms per step):
+        // 1,3,6,12,9,1 17.94; 2,6,12,11,1 17.95; 1,2,4,8,16,1 18.21; 1,3,9,18,1 18.12; 1,4,8,18,1 18.19; no tail (1,3,6,12,10) 18.28.
         const bool tail = nframes >= 4;
         const int body_end = tail ? nframes - 1 : nframes;
-        const int cap = 16;  // larger chunks only lengthen the download that is still pending when the last kernel ends
-        for (int f = 0, c = 1; f < body_end; f += c, c = std::min(2 * c, cap)) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
+        const int cap = 12;  // larger chunks only lengthen the download that is still pending when the last kernel ends
+        for (int f = 0, c = 1; f < body_end; f += c, c = c == 1 ? 3 : std::min(2 * c, cap)) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
         if (tail) plan.emplace_back(nframes - 1, 1);
     } else {
         const int chunk = std::max(1, std::min(h->host_chunk, nframes));
