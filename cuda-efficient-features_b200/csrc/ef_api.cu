@@ -166,6 +166,8 @@ struct ef_handle {
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_blur = false;  // measured: +0.3 % (5.181 vs 5.195 ms per 8 frames) -- the blur saturates the GPU by itself, the short kernels only queue behind it
+    int slot0 = 0;              // first workspace slot of the call being enqueued (host pipeline: chunks on alternating streams use disjoint slots)
+    int host_streams = 2;       // host-buffer pipeline: chunks alternate between the caller's stream and s_side (EF_B200_HOST_STREAMS=1: one stream)
     int host_chunk = 0;         // frames per chunk of the host-buffer pipeline; 0 = geometric plan 1, 2, 4, ... (measured: 10.43 vs 10.52 ms per 16 frames for chunks of 4)
 
     // optional per-stage timing (bench.py): events recorded between the stages
@@ -176,7 +178,7 @@ struct ef_handle {
 
     // tensor maps of the current geometry (re-encoded only when the caller's image, its layout or the frame size changes)
     EfTmaMaps tma;
-    const void* tma_img0 = nullptr; size_t tma_stride = 0; int tma_pitch = 0, tma_w = 0, tma_h = 0, tma_nframes = 0;
+    const void* tma_img0 = nullptr; const void* tma_ws = nullptr; size_t tma_stride = 0; int tma_pitch = 0, tma_w = 0, tma_h = 0, tma_nframes = 0;
 
     // last call
     int last_w = 0, last_h = 0, last_nframes = 0;
@@ -485,6 +487,7 @@ int allocate(ef_handle* h)
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     EF_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     if (const char* e = std::getenv("EF_B200_OVERLAP_BLUR")) h->overlap_blur = std::atoi(e) != 0;   // 1: blur on the side stream (A/B switch)
+    if (const char* e = std::getenv("EF_B200_HOST_STREAMS")) h->host_streams = std::atoi(e) == 1 ? 1 : 2;
     if (const char* e = std::getenv("EF_B200_HOST_CHUNK")) h->host_chunk = std::max(0, std::atoi(e)); // frames per pipeline chunk of the host API (0: geometric plan)
     h->ev_in.resize(p.max_batch); h->ev_cnt.resize(p.max_batch);
     for (int i = 0; i < p.max_batch; i++) {
@@ -514,8 +517,9 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
     P.shard_i = 0; P.shard_n = 1; P.select_from_counters = 0;
     P.desc_row0 = 0; P.desc_rows = 0x7fffffff; P.blur_by_slice = 0; P.slice_y = h->d_slice_y;
     P.desc_type = p.desc_type; P.desc_bytes = desc_bytes_of(p.desc_type);
-    P.ws = h->d_ws; P.ws_stride = h->slot_bytes;
-    P.counters = h->d_counters;
+    if (h->slot0 < 0 || h->slot0 + nframes > p.max_batch) return fail(h, EF_ERR_CAPACITY, "internal: workspace slots");
+    P.ws = h->d_ws + (size_t)h->slot0 * h->slot_bytes; P.ws_stride = h->slot_bytes;
+    P.counters = h->d_counters + (size_t)h->slot0 * EF_MAX_LEVELS;
     int tiles = 0, btiles = 0, bands = 0, kblocks = 0, sblocks = 0, strips = 0;
     for (int l = 0; l < p.nlevels; l++) {
         EfLevel& L = P.lv[l];
@@ -564,7 +568,7 @@ int build_pipe(ef_handle* h, int nframes, int w, int hh, EfPipe& P, int shard_i 
 const EfTmaMaps* prepare_tma(ef_handle* h, const EfPipe& P)
 {
     if (h->tma_img0 == P.img0 && h->tma_stride == P.img0_stride && h->tma_pitch == P.img0_pitch && h->tma_w == P.lv[0].w && h->tma_h == P.lv[0].h &&
-        h->tma_nframes == P.nframes) return &h->tma;
+        h->tma_nframes == P.nframes && h->tma_ws == (const void*)P.ws) return &h->tma;
     h->tma.blur_src_ok = 0; h->tma.resize_src_ok = 0;
     for (int l = 1; l < P.nlevels; l++) {
         // source of pyramid level l = level l-1.  The TMA kernel zero-fills what lies outside the source instead of clamping the
@@ -584,7 +588,7 @@ const EfTmaMaps* prepare_tma(ef_handle* h, const EfPipe& P)
         const size_t pitch = l == 0 ? (size_t)P.img0_pitch : (size_t)L.img_pitch, stride = l == 0 ? (size_t)P.img0_stride : (size_t)P.ws_stride;
         if (ef_tma_encode_u8(&h->tma.blur_src[l], base, L.w, L.h, P.nframes, pitch, stride, EF_BLUR_BOX_W, EF_BLUR_BOX_H)) h->tma.blur_src_ok |= 1u << l;
     }
-    h->tma_img0 = P.img0; h->tma_stride = P.img0_stride; h->tma_pitch = P.img0_pitch; h->tma_w = P.lv[0].w; h->tma_h = P.lv[0].h; h->tma_nframes = P.nframes;
+    h->tma_img0 = P.img0; h->tma_ws = P.ws; h->tma_stride = P.img0_stride; h->tma_pitch = P.img0_pitch; h->tma_w = P.lv[0].w; h->tma_h = P.lv[0].h; h->tma_nframes = P.nframes;
     return &h->tma;
 }
 
@@ -603,8 +607,10 @@ void mark(ef_handle* h, int stage, cudaStream_t s)
 
 int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
 {
-    EF_CUDA(h, cudaMemset2DAsync(h->d_ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
-    EF_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
+    EF_CUDA(h, cudaMemset2DAsync(P.ws, h->slot_bytes, 0, h->rowcnt_bytes, P.nframes, s));
+    EF_CUDA(h, cudaMemsetAsync(P.counters, 0, sizeof(EfLevelCounters) * EF_MAX_LEVELS * P.nframes, s));
+    uint8_t* const sift128 = h->d_sift128 + (size_t)h->slot0 * P.nfeatures * 128;
+    float* const proj = h->keep_proj ? h->d_proj + (size_t)h->slot0 * P.nfeatures * 512 : nullptr;
     mark(h, -1, s);
     ef_launch_pyramid(P, prepare_tma(h, P), s);      mark(h, EF_STAGE_PYRAMID, s);
     ef_launch_score(P, s);        mark(h, EF_STAGE_SCORE, s);
@@ -634,11 +640,11 @@ int run_pipeline(ef_handle* h, EfPipe& P, bool want_desc, cudaStream_t s)
             mark(h, EF_STAGE_DESCRIBE, s);
         } else {
             EfHashSiftTables t{ h->d_exp_table, h->d_grad_table };
-            ef_launch_hashsift_features_pipe(P, t, h->d_sift128, s);
+            ef_launch_hashsift_features_pipe(P, t, sift128, s);
             mark(h, EF_STAGE_DESCRIBE, s);
             const EfProjTables pt{ h->d_hs_bfrag[v], h->d_hs_bias[v], h->hs_shift[v], h->d_hs_weights_t[v], h->d_hs_btc[v], h->hs_ndig[v] };
-            ef_launch_hashsift_project_batch(h->d_sift128, P.nfeatures, P.counts, P.nframes, pt, P.desc_bytes * 8,
-                                             P.desc, (size_t)P.desc_stride, P.desc_pitch, h->keep_proj ? h->d_proj : nullptr, s);
+            ef_launch_hashsift_project_batch(sift128, P.nfeatures, P.counts, P.nframes, pt, P.desc_bytes * 8,
+                                             P.desc, (size_t)P.desc_stride, P.desc_pitch, proj, s);
             mark(h, EF_STAGE_PROJECT, s);
         }
     }
@@ -875,10 +881,15 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
         // uploaded while the previous (smaller) one computes, launches per frame fall -- and a one-frame tail, so that only 2.5 MB of
         // results are still to be downloaded when the last kernel ends.  Measured at 32 frames (tools/gpu_e2e_plan.sh, ms per step):
         // 1,3,6,12,9,1 17.94; 2,6,12,11,1 17.95; 1,2,4,8,16,1 18.21; 1,3,9,18,1 18.12; 1,4,8,18,1 18.19; no tail (1,3,6,12,10) 18.28.
+        // On two alternating compute streams (below) the chunk boundaries overlap and small chunks cost less: 1, 2, 4, 4, ... + tail
+        // (17.51 ms; 1,3,6,6,6,6,3,1 17.54; 1,3,6,12,9,1 17.76; 1,2,4,8,16,1 17.94).
         const bool tail = nframes >= 4;
         const int body_end = tail ? nframes - 1 : nframes;
-        const int cap = 12;  // larger chunks only lengthen the download that is still pending when the last kernel ends
-        for (int f = 0, c = 1; f < body_end; f += c, c = c == 1 ? 3 : std::min(2 * c, cap)) { c = std::min(c, body_end - f); plan.emplace_back(f, c); }
+        const bool two_streams = h->host_streams == 2 && !h->overlap_blur && h->s_side;
+        const int cap = two_streams ? 4 : 12;  // larger chunks only lengthen the download that is still pending when the last kernel ends
+        for (int f = 0, c = 1; f < body_end; f += c, c = two_streams ? std::min(2 * c, cap) : (c == 1 ? 3 : std::min(2 * c, cap))) {
+            c = std::min(c, body_end - f); plan.emplace_back(f, c);
+        }
         if (tail) plan.emplace_back(nframes - 1, 1);
     } else {
         const int chunk = std::max(1, std::min(h->host_chunk, nframes));
@@ -898,17 +909,26 @@ int ef_detect_and_compute_host_batch(ef_handle* h, int nframes, const uint8_t* h
             EF_CUDA(h, cudaMemcpy2DAsync(h->d_in + f * h->in_stride, h->in_pitch, h_imgs + f * img_stride, pitch, width, height, cudaMemcpyHostToDevice, h->s_in));
         EF_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
     }
+    // Chunks alternate between the caller's stream and a second one, each in its own workspace slots [f0, f0 + n): the short, latency-bound
+    // launches at the end of one chunk (compaction, selection, angles, the tail of the descriptor kernels) and at the start of the next (the
+    // seven dependent pyramid launches) then run next to the other chunk's throughput-bound kernels instead of in front of an idle GPU.
+    const bool two = h->host_streams == 2 && nchunks >= 3 && !h->overlap_blur && h->s_side;
+    if (two) { EF_CUDA(h, cudaEventRecord(h->ev_fork, s)); EF_CUDA(h, cudaStreamWaitEvent(h->s_side, h->ev_fork, 0)); }
     for (int c = 0; c < nchunks; c++) {
         const int f0 = plan[c].first, n = plan[c].second;
-        EF_CUDA(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
+        cudaStream_t cs = (two && (c & 1)) ? h->s_side : s;
+        EF_CUDA(h, cudaStreamWaitEvent(cs, h->ev_in[c], 0));
+        h->slot0 = two ? f0 : 0;
         int rc = ef_detect_and_compute_batch_async(h, n, h->d_in + f0 * h->in_stride, h->in_stride, h->in_pitch, width, height,
                                                    (float*)((uint8_t*)h->d_out_kpts + f0 * h->out_kpts_stride), h->out_kpts_stride, h->out_kpts_pitch,
                                                    h_desc ? h->d_out_desc + f0 * h->out_desc_stride : nullptr, h->out_desc_stride, (size_t)db,
-                                                   h->d_out_counts + f0, s);
-        if (rc != EF_OK) { cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(s); return rc; }
-        EF_CUDA(h, cudaMemcpyAsync(h->h_counts_pinned + f0, h->d_out_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
-        EF_CUDA(h, cudaEventRecord(h->ev_cnt[c], s));
+                                                   h->d_out_counts + f0, cs);
+        h->slot0 = 0;
+        if (rc != EF_OK) { cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(s); if (two) cudaStreamSynchronize(h->s_side); return rc; }
+        EF_CUDA(h, cudaMemcpyAsync(h->h_counts_pinned + f0, h->d_out_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, cs));
+        EF_CUDA(h, cudaEventRecord(h->ev_cnt[c], cs));
     }
+    if (two) { EF_CUDA(h, cudaEventRecord(h->ev_join, h->s_side)); EF_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0)); }
     for (int c = 0; c < nchunks; c++) {
         // one host wait per chunk to size the outputs (the reference blocks 16 times per frame); later chunks keep running
         EF_CUDA(h, cudaEventSynchronize(h->ev_cnt[c]));
